@@ -1,0 +1,184 @@
+/* slam_b200.h — C ABI of libslam_b200.so: the B200 (sm_100a) kernels behind the SLAM-LLM
+ * training-step hot path (SURVEY.md §8a rows a1–a9).
+ *
+ * The reference (X-LANCE/SLAM-LLM) has NO native boundary: its hot path is PyTorch eager calls
+ * into whisper / transformers / peft.  Each entry point below therefore cites the reference
+ * Python call site (path:line under /root/reference) whose arithmetic it replaces; the Python
+ * host mirror (src/slam_llm/…, slam_llm_b200/…) binds them through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - tensors are row-major, innermost dimension contiguous, leading dimension in ELEMENTS;
+ *   - bf16 = __nv_bfloat16 storage, f32 = float, i64 = int64_t, u8 = unsigned char;
+ *   - return value: 0 on success, non-zero cudaError_t (or negative slam error) on failure;
+ *     slam_last_error() returns a human-readable string for the last failure on this thread;
+ *   - no entry point allocates, frees or synchronises: workspaces are caller-provided.
+ */
+#ifndef SLAM_B200_H_
+#define SLAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAM_B200_ABI_VERSION 1
+
+int slam_abi_version(void);
+const char* slam_last_error(void);
+/* number of kernel launches issued through this library since process start (bench "gpu_launches") */
+int64_t slam_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM core (tcgen05 + TMEM accumulators, TMA-fed, persistent, warp-specialised).
+ *   out[M,N] = act( alpha * ( A[M,K1]·B[N,K1]^T  +  A2[M,K2]·B2[N,K2]^T ) + bias[N] ) + residual[M,N]
+ * Both operands are K-major bf16.  The optional second K-segment (A2,B2) is accumulated into the
+ * SAME TMEM tile as the base product before the epilogue: this is the fused LoRA path, with
+ * A2 = x·A_lora^T (rank-padded to a multiple of 64) and B2 = (alpha/r)·B_lora.
+ * Replaces: F.linear in whisper/transformers + peft lora.Linear.forward
+ *   (models/slam_model.py:214-218,400; models/encoder.py:26-27; models/projector.py:20-26).
+ * -------------------------------------------------------------------------------------------*/
+typedef struct slam_gemm_args {
+  const void* a;   int64_t lda;   /* bf16 [M,K1] */
+  const void* b;   int64_t ldb;   /* bf16 [N,K1] */
+  int32_t k1;
+  int32_t k2;                     /* 0 = no second segment */
+  const void* a2;  int64_t lda2;  /* bf16 [M,K2] */
+  const void* b2;  int64_t ldb2;  /* bf16 [N,K2] */
+  void* out;       int64_t ldo;   /* bf16 or f32 [M,N] */
+  int32_t out_f32;                /* 0: bf16 out, 1: f32 out */
+  int32_t act;                    /* 0 none, 1 GELU(erf), 2 ReLU */
+  const float* bias;              /* f32 [N] or NULL */
+  const void* residual; int64_t ldr; /* bf16 [M,N] or NULL; added after activation */
+  float alpha;
+  int32_t m, n;
+  int32_t block_n;                /* 0 = auto; else 64/128/256 */
+} slam_gemm_args;
+int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
+
+/* C[P,Q] (f32) = scale * sum_m A[m,P] * B[m,Q]   (thin weight-gradient product: P <= 64)
+ * Used for LoRA dA / dB (peft lora.Linear backward) and bias gradients.  C is OVERWRITTEN. */
+int slam_wgrad_thin(const void* a_bf16, int64_t lda, int32_t p, const void* b_bf16, int64_t ldb,
+                    int32_t q, int32_t m, float scale, float* c, int64_t ldc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  log-mel front end.  whisper.pad_or_trim + whisper.log_mel_spectrogram(...).permute(1,0)
+ *     as called at datasets/speech_dataset.py:101-103.
+ *   wav      f32 [B, n_samples]  (already padded/trimmed; n_frames = n_samples/160)
+ *   filters_t f32 [201, n_mels]  (slaney mel filterbank, TRANSPOSED so mel is the contiguous axis)
+ *   out      f32 [B, n_frames, n_mels]
+ *   scratch  f32 [B]  per-utterance running max (written by the kernel)
+ * -------------------------------------------------------------------------------------------*/
+int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, const float* filters_t,
+                int32_t n_mels, float* out, float* scratch_max, void* stream);
+
+/* a2  Whisper conv stem helpers (models/encoder.py:18-24).  Time-major activations.
+ *   im2col for Conv1d(k=3, pad=1, stride s): x[B,T,C] (f32 or bf16) -> col bf16 [B*T_out, ldk]
+ *   with col[b,t,(kk*C + c)] = x[b, s*t + kk - 1, c] (zero outside); columns >= 3C zero-filled. */
+int slam_conv_im2col(const void* x, int32_t x_is_f32, int32_t batch, int32_t t_in, int32_t c,
+                     int32_t stride, void* col_bf16, int64_t ldk, void* stream);
+/* y[b,t,:] = x[b,t,:] + pos[t,:]  (bf16 x, f32 pos) — models/encoder.py:24 */
+int slam_add_pos(void* x_bf16, const float* pos, int32_t batch, int32_t t, int32_t d, void* stream);
+
+/* LayerNorm over last dim (fp32 statistics), whisper LayerNorm / ln_post (models/encoder.py:26-29). */
+int slam_layernorm(const void* x_bf16, const float* w, const float* b, void* y_bf16, int32_t rows,
+                   int32_t d, float eps, void* stream);
+
+/* Multi-head attention forward (flash-style, online softmax, bf16 in / fp32 accumulate).
+ *   q [B,Sq,Hq,dh], k/v [B,Sk,Hkv,dh] given as base pointers + row strides (elements) so that the
+ *   fused QKV buffer can be used in place.  causal: 0/1.  key_mask u8 [B,Sk] (1 = attend) or NULL.
+ *   lse f32 [B,Hq,Sq] (log-sum-exp, natural log) or NULL.  out bf16 [B,Sq,Hq,dh] with row stride ldo.
+ * Replaces whisper MultiHeadAttention.qkv_attention and HF LlamaAttention (eager softmax). */
+typedef struct slam_attn_args {
+  const void* q; int64_t ldq;   /* row stride between consecutive tokens, elements */
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* out;     int64_t ldo;
+  float* lse;
+  const uint8_t* key_mask;
+  int32_t batch, sq, sk, hq, hkv, dh;
+  int32_t causal;
+  float scale;
+  /* backward only */
+  const void* dout; int64_t lddo;
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+  float* delta;                  /* f32 [B,Hq,Sq] scratch */
+  float* dq_accum;               /* f32 scratch [B,Sq,Hq,dh]: dQ partial sums (zeroed by the call) */
+} slam_attn_args;
+int slam_attn_fwd(const slam_attn_args* a, void* stream);
+int slam_attn_bwd(const slam_attn_args* a, void* stream);
+
+/* a4  embedding gather + modality merge (models/slam_model.py:370-392).
+ *   ids i64 [B,S] (-1 treated as 0), modality_mask u8 [B,S], audio bf16 [B,Ta,D],
+ *   embed bf16 [V,D] -> x bf16 [B,S,D].  Semantics follow the reference loop exactly:
+ *   start = argmax(mask), len = min(sum(mask), Ta); rows start..start+len-1 take audio rows;
+ *   every other row r takes embed[ids[r]] * (mask[r] ? 0 : 1). */
+int slam_embed_merge(const int64_t* ids, const uint8_t* modality_mask, const void* audio_bf16,
+                     int32_t ta, const void* embed_bf16, void* x_bf16, int32_t batch, int32_t s,
+                     int32_t d, void* stream);
+/* backward of the merge wrt the audio rows: daudio[b,j,:] = dx[b,start+j,:] for j < len, else 0 */
+int slam_embed_merge_bwd(const uint8_t* modality_mask, const void* dx_bf16, void* daudio_bf16,
+                         int32_t ta, int32_t batch, int32_t s, int32_t d, void* stream);
+
+/* a5  Llama decoder element-wise kernels (HF LlamaRMSNorm / apply_rotary_pos_emb / LlamaMLP). */
+int slam_rmsnorm_fwd(const void* x_bf16, const void* w_bf16, void* y_bf16, float* rstd, int32_t rows,
+                     int32_t d, float eps, void* stream);
+/* dx = rmsnorm_bwd(dy; x, w, rstd) (+ dres if non-NULL): fuses the residual-stream gradient add */
+int slam_rmsnorm_bwd(const void* dy_bf16, const void* x_bf16, const void* w_bf16, const float* rstd,
+                     const void* dres_bf16, void* dx_bf16, int32_t rows, int32_t d, void* stream);
+/* in-place rotate-half RoPE on heads laid out [rows, n_heads, dh] with row stride ld; position =
+ * row % seq_len; cos/sin are f32 [seq_len, dh/2] tables (host builds them exactly like
+ * LlamaRotaryEmbedding); inverse != 0 applies the transpose rotation (backward). */
+int slam_rope(void* x_bf16, int64_t ld, int32_t rows, int32_t seq_len, int32_t n_heads, int32_t dh,
+              const float* cos_table, const float* sin_table, int32_t inverse, void* stream);
+/* h = silu(g) * u with gu = [g | u] bf16 [rows, 2F] */
+int slam_swiglu_fwd(const void* gu_bf16, void* h_bf16, int32_t rows, int32_t f, void* stream);
+int slam_swiglu_bwd(const void* gu_bf16, const void* dh_bf16, void* dgu_bf16, int32_t rows, int32_t f,
+                    void* stream);
+
+/* a7  token cross-entropy + accuracy on fp32 logits rows (HF ForCausalLMLoss + utils/metric.py:3-20).
+ *   logits f32 [R,V] (rows already shifted/selected by the host), targets i64 [R] (-100 = ignore).
+ *   Outputs: loss_sum f32[1], n_valid i32 [1], n_correct i32 [1] (atomically accumulated: caller
+ *   zeroes), and dlogits bf16 [R,V] = (softmax - onehot) * grad_scale[0] for valid rows, else 0.
+ *   grad_scale is read from device memory so the 1/n_valid factor needs no host sync. */
+int slam_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets, int32_t rows,
+                       int32_t vocab, float* loss_sum, int32_t* n_valid, int32_t* n_correct,
+                       void* dlogits_bf16, int64_t lddl, const float* grad_scale, void* stream);
+
+/* a8  AdamW on one flat f32 parameter buffer (torch.optim.AdamW, pipeline/finetune.py:247-251).
+ *   step_host is the 1-based optimizer step; grad_div divides the gradient first (DDP mean). */
+int slam_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+               float beta1, float beta2, float eps, float weight_decay, int32_t step_host, float grad_div,
+               void* stream);
+
+/* utility kernels */
+int slam_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, float scale, void* stream);
+int slam_cast_bf16_to_f32(const void* x_bf16, float* y, int64_t n, void* stream);
+/* y[C,R] = x[R,C]^T (bf16) */
+int slam_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                        void* stream);
+/* y[i,:] = x[idx[i],:]  /  y[idx[i],:] = x[i,:] (rows of d bf16; idx i32) */
+int slam_gather_rows(const void* x_bf16, const int32_t* idx, void* y_bf16, int32_t n_idx, int32_t d,
+                     void* stream);
+int slam_scatter_rows(const void* x_bf16, const int32_t* idx, void* y_bf16, int32_t n_idx, int32_t d,
+                      void* stream);
+/* relu backward: dx = dy * (y > 0) ; bf16 */
+int slam_relu_bwd(const void* dy_bf16, const void* y_bf16, void* dx_bf16, int64_t n, void* stream);
+/* column sums: out[c] = sum_r x[r,c] (bf16 in, f32 out) — bias gradients */
+int slam_colsum(const void* x_bf16, int64_t ldx, int32_t rows, int32_t cols, float* out, void* stream);
+/* batched strided cast with optional transpose (packs LoRA adapters into rank-padded GEMM operands):
+ *   dst[b][i][j] = scale*src[b][i][j]   (transpose == 0)    dst[b][j][i] = scale*src[b][i][j]  (transpose != 0) */
+int slam_pack2d(const float* src, int64_t src_batch_stride, int64_t src_ld, void* dst_bf16,
+                int64_t dst_batch_stride, int64_t dst_ld, int32_t batch, int32_t rows, int32_t cols,
+                float scale, int32_t transpose, void* stream);
+/* y = a + b (bf16) */
+int slam_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_B200_H_ */

@@ -1,0 +1,509 @@
+// Flash-style multi-head attention forward + backward (bf16 in, fp32 accumulate, online softmax),
+// never materialising the [S,S] score matrix (the reference's HF-4.35 eager LlamaAttention and
+// whisper's qkv_attention do).
+//   - encoder: non-causal, no mask, dh = 64, forward only (models/encoder.py:26-27);
+//   - decoder: causal + key-padding mask, GQA (Hq = g * Hkv) without repeat_kv copies, dh = 64/128,
+//     forward + backward (dQ, dK, dV) with the log-sum-exp saved by the forward.
+// Round-1 implementation: warp-level mma.sync.m16n8k16 tensor-core tiles with ldmatrix-fed
+// fragments (attention is ~1.5 % of decoder FLOPs at S≈400; the tcgen05 path is reserved for the GEMMs).
+#include <math_constants.h>
+
+#include "../../include/slam_b200.h"
+#include "common.cuh"
+#include "host.cuh"
+
+namespace slam {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnP {
+  const bf16* q; long long ldq;
+  const bf16* k; long long ldk;
+  const bf16* v; long long ldv;
+  bf16* out; long long ldo;
+  float* lse;
+  const uint8_t* key_mask;
+  int batch, sq, sk, hq, hkv;
+  int causal;
+  float scale;
+  const bf16* dout; long long lddo;
+  bf16* dq; long long lddq;
+  bf16* dk; long long lddk;
+  bf16* dv; long long lddv;
+  float* delta;
+  float* dq_accum;
+};
+
+// rows x DH bf16 tile, global (row stride ld) -> shared (row pitch DH+8); rows >= valid are zero-filled
+template <int DH, int ROWS, int THREADS>
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long ld, int valid) {
+  constexpr int PITCH = DH + 8;
+  constexpr int VPR = DH / 8;
+  for (int i = threadIdx.x; i < ROWS * VPR; i += THREADS) {
+    const int r = i / VPR, c = (i - r * VPR) * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < valid) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * PITCH + c) = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- forward
+template <int DH>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
+  constexpr int BM = 64, BN = 64, PITCH = DH + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + BM * PITCH;
+  bf16* sV = sK + BN * PITCH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.hq / p.hkv);
+  const int q0 = blockIdx.x * BM;
+
+  load_tile<DH, BM, 128>(sQ, p.q + (static_cast<long long>(b) * p.sq + q0) * p.ldq + h * DH, p.ldq, min(BM, p.sq - q0));
+  __syncthreads();
+  uint32_t qf[DH / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks)
+    ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ks * 16 + (lane >> 4) * 8);
+
+  float o[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+  float mrow[2] = {-CUDART_INF_F, -CUDART_INF_F};
+  float lrow[2] = {0.0f, 0.0f};
+  const float scale_log2 = p.scale * kLog2e;
+  const int n_end = p.causal ? min(p.sk, q0 + BM) : p.sk;
+  const bf16* kbase = p.k + static_cast<long long>(b) * p.sk * p.ldk + hk * DH;
+  const bf16* vbase = p.v + static_cast<long long>(b) * p.sk * p.ldv + hk * DH;
+  const uint8_t* mk = p.key_mask != nullptr ? p.key_mask + static_cast<long long>(b) * p.sk : nullptr;
+
+  for (int n0 = 0; n0 < n_end; n0 += BN) {
+    __syncthreads();
+    load_tile<DH, BN, 128>(sK, kbase + static_cast<long long>(n0) * p.ldk, p.ldk, min(BN, p.sk - n0));
+    load_tile<DH, BN, 128>(sV, vbase + static_cast<long long>(n0) * p.ldv, p.ldv, min(BN, p.sk - n0));
+    __syncthreads();
+
+    float s[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+#pragma unroll
+      for (int nb2 = 0; nb2 < BN / 16; ++nb2) {
+        uint32_t kb[4];
+        ldsm_x4(kb, sK + (nb2 * 16 + (lane & 7) + (lane >> 4) * 8) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(s[2 * nb2], qf[ks], kb[0], kb[1]);
+        mma16816(s[2 * nb2 + 1], qf[ks], kb[2], kb[3]);
+      }
+    }
+    // scale + mask (log2 domain)
+#pragma unroll
+    for (int nb = 0; nb < BN / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = n0 + nb * 8 + 2 * (lane & 3) + (e & 1);
+        const int row = q0 + warp * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+        bool ok = col < p.sk && (!p.causal || col <= row);
+        if (ok && mk != nullptr) ok = mk[col] != 0;
+        s[nb][e] = ok ? s[nb][e] * scale_log2 : -CUDART_INF_F;
+      }
+    }
+    // online softmax, two rows per thread
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * r], s[nb][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(mrow[r], mx);
+      const float m_safe = m_new == -CUDART_INF_F ? 0.0f : m_new;
+      const float corr = exp2f(mrow[r] - m_safe);
+      mrow[r] = m_new;
+      float rs = 0.0f;
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) {
+        const float p0 = exp2f(s[nb][2 * r] - m_safe);
+        const float p1 = exp2f(s[nb][2 * r + 1] - m_safe);
+        s[nb][2 * r] = p0;
+        s[nb][2 * r + 1] = p1;
+        rs += p0 + p1;
+      }
+      lrow[r] = lrow[r] * corr + rs;
+#pragma unroll
+      for (int i = 0; i < DH / 8; ++i) {
+        o[i][2 * r] *= corr;
+        o[i][2 * r + 1] *= corr;
+      }
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nb2 = 0; nb2 < DH / 16; ++nb2) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + nb2 * 16 + (lane >> 4) * 8);
+        mma16816(o[2 * nb2], a, vb[0], vb[1]);
+        mma16816(o[2 * nb2 + 1], a, vb[2], vb[3]);
+      }
+    }
+  }
+
+  // finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = lrow[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+    const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+    if (row < p.sq) {
+      bf16* orow = p.out + (static_cast<long long>(b) * p.sq + row) * p.ldo + h * DH;
+#pragma unroll
+      for (int i = 0; i < DH / 8; ++i) {
+        const uint32_t pk = pack_bf16x2(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * (lane & 3)) = pk;
+      }
+      if (p.lse != nullptr && (lane & 3) == 0) {
+        // fully masked row: lse = 0 keeps exp(s - lse) = 0 in the backward (s = -inf there)
+        const float lse = l > 0.0f ? mrow[r] * kLn2 + logf(l) : 0.0f;
+        p.lse[(static_cast<long long>(b) * p.hq + h) * p.sq + row] = lse;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+__global__ void attn_delta_kernel(const AttnP p, int dh) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = p.batch * p.sq * p.hq;
+  if (warp_global >= total) return;
+  const int h = warp_global % p.hq;
+  const long long tok = warp_global / p.hq;  // b * sq + i
+  const bf16* o = p.out + tok * p.ldo + h * dh;
+  const bf16* d = p.dout + tok * p.lddo + h * dh;
+  float acc = 0.0f;
+  for (int c = lane * 2; c < dh; c += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + c));
+    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + c));
+    acc += a.x * g.x + a.y * g.y;
+  }
+  acc = warp_sum(acc);
+  const int b = static_cast<int>(tok / p.sq), i = static_cast<int>(tok % p.sq);
+  if (lane == 0) p.delta[(static_cast<long long>(b) * p.hq + h) * p.sq + i] = acc;
+}
+
+// One CTA = 64 keys of one (batch, kv head); loops over the q heads of the group and over query blocks.
+// Each warp owns 16 keys: dK/dV accumulate in registers (no atomics, GQA-summed in place);
+// dQ partials go through fp32 atomics into dq_accum (as FlashAttention-2 does).
+template <int DH, int BQ>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
+  constexpr int BN = 64, PITCH = DH + 8, SPITCH = BQ + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sV = sK + BN * PITCH;
+  bf16* sQ = sV + BN * PITCH;
+  bf16* sdO = sQ + BQ * PITCH;
+  bf16* sdS = sdO + BQ * PITCH;  // [key][q]
+  float* sLse = reinterpret_cast<float*>(sdS + BN * SPITCH);
+  float* sDelta = sLse + BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hk = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * BN;
+  const int group = p.hq / p.hkv;
+  const float scale_log2 = p.scale * kLog2e;
+
+  load_tile<DH, BN, 128>(sK, p.k + (static_cast<long long>(b) * p.sk + k0) * p.ldk + hk * DH, p.ldk, min(BN, p.sk - k0));
+  load_tile<DH, BN, 128>(sV, p.v + (static_cast<long long>(b) * p.sk + k0) * p.ldv + hk * DH, p.ldv, min(BN, p.sk - k0));
+
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.0f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.0f;
+  }
+  // key validity for the two key rows this thread owns in the transposed score tile
+  bool key_ok[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = k0 + warp * 16 + (lane >> 2) + r * 8;
+    key_ok[r] = key < p.sk && (p.key_mask == nullptr || p.key_mask[static_cast<long long>(b) * p.sk + key] != 0);
+  }
+
+  const int q_start = p.causal ? (k0 / BQ) * BQ : 0;
+  for (int g = 0; g < group; ++g) {
+    const int h = hk * group + g;
+    for (int q0 = q_start; q0 < p.sq; q0 += BQ) {
+      __syncthreads();
+      const int vq = min(BQ, p.sq - q0);
+      load_tile<DH, BQ, 128>(sQ, p.q + (static_cast<long long>(b) * p.sq + q0) * p.ldq + h * DH, p.ldq, vq);
+      load_tile<DH, BQ, 128>(sdO, p.dout + (static_cast<long long>(b) * p.sq + q0) * p.lddo + h * DH, p.lddo, vq);
+      for (int i = threadIdx.x; i < BQ; i += 128) {
+        const long long off = (static_cast<long long>(b) * p.hq + h) * p.sq + q0 + i;
+        sLse[i] = i < vq ? p.lse[off] * kLog2e : 0.0f;
+        sDelta[i] = i < vq ? p.delta[off] : 0.0f;
+      }
+      __syncthreads();
+
+      // S^T = K_w Q^T and dP^T = V_w dO^T   (16 keys x BQ queries per warp)
+      float st[BQ / 8][4], dpt[BQ / 8][4];
+#pragma unroll
+      for (int i = 0; i < BQ / 8; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.0f;
+        dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.0f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) {
+        uint32_t ka[4], va[4];
+        const int arow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int acol = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(ka, sK + arow * PITCH + acol);
+        ldsm_x4(va, sV + arow * PITCH + acol);
+#pragma unroll
+        for (int nb2 = 0; nb2 < BQ / 16; ++nb2) {
+          uint32_t qb[4], ob[4];
+          const int brow = nb2 * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int bcol = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(qb, sQ + brow * PITCH + bcol);
+          ldsm_x4(ob, sdO + brow * PITCH + bcol);
+          mma16816(st[2 * nb2], ka, qb[0], qb[1]);
+          mma16816(st[2 * nb2 + 1], ka, qb[2], qb[3]);
+          mma16816(dpt[2 * nb2], va, ob[0], ob[1]);
+          mma16816(dpt[2 * nb2 + 1], va, ob[2], ob[3]);
+        }
+      }
+      // P^T and dS^T in place; write dS^T (bf16) to shared [key][q]
+#pragma unroll
+      for (int nb = 0; nb < BQ / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const int key = k0 + warp * 16 + (lane >> 2) + r * 8;
+          const int ql = nb * 8 + 2 * (lane & 3) + (e & 1);
+          const int qi = q0 + ql;
+          const bool ok = key_ok[r] && qi < p.sq && (!p.causal || key <= qi);
+          const float pv = ok ? exp2f(st[nb][e] * scale_log2 - sLse[ql]) : 0.0f;
+          const float ds = pv * (dpt[nb][e] - sDelta[ql]) * p.scale;
+          st[nb][e] = pv;
+          dpt[nb][e] = ds;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int krow = warp * 16 + (lane >> 2) + r * 8;
+          *reinterpret_cast<uint32_t*>(sdS + krow * SPITCH + nb * 8 + 2 * (lane & 3)) = pack_bf16x2(dpt[nb][2 * r], dpt[nb][2 * r + 1]);
+        }
+      }
+      // dV += P^T dO ; dK += dS^T Q   (contraction over the BQ queries)
+#pragma unroll
+      for (int kk = 0; kk < BQ / 16; ++kk) {
+        uint32_t pa[4], da[4];
+        pa[0] = pack_bf16x2(st[2 * kk][0], st[2 * kk][1]);
+        pa[1] = pack_bf16x2(st[2 * kk][2], st[2 * kk][3]);
+        pa[2] = pack_bf16x2(st[2 * kk + 1][0], st[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+        da[0] = pack_bf16x2(dpt[2 * kk][0], dpt[2 * kk][1]);
+        da[1] = pack_bf16x2(dpt[2 * kk][2], dpt[2 * kk][3]);
+        da[2] = pack_bf16x2(dpt[2 * kk + 1][0], dpt[2 * kk + 1][1]);
+        da[3] = pack_bf16x2(dpt[2 * kk + 1][2], dpt[2 * kk + 1][3]);
+#pragma unroll
+        for (int nb2 = 0; nb2 < DH / 16; ++nb2) {
+          uint32_t ob[4], qb[4];
+          const int brow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int bcol = nb2 * 16 + (lane >> 4) * 8;
+          ldsm_x4_t(ob, sdO + brow * PITCH + bcol);
+          ldsm_x4_t(qb, sQ + brow * PITCH + bcol);
+          mma16816(dv[2 * nb2], pa, ob[0], ob[1]);
+          mma16816(dv[2 * nb2 + 1], pa, ob[2], ob[3]);
+          mma16816(dk[2 * nb2], da, qb[0], qb[1]);
+          mma16816(dk[2 * nb2 + 1], da, qb[2], qb[3]);
+        }
+      }
+      __syncthreads();
+      // dQ[BQ x DH] += dS[BQ x 64] K[64 x DH]: warp -> (query block of 16, DH slice)
+      {
+        constexpr int QB = BQ / 16;          // query 16-blocks
+        constexpr int SL = 4 / QB;           // DH slices
+        constexpr int DSL = DH / SL;         // slice width
+        const int qb_i = warp % QB, sl = warp / QB;
+        float dq[DSL / 8][4];
+#pragma unroll
+        for (int i = 0; i < DSL / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          uint32_t a[4];
+          // A = dS (q x key) read transposed from sdS[key][q]
+          ldsm_x4_t(a, sdS + (kk * 16 + (lane & 7) + (lane >> 4) * 8) * SPITCH + qb_i * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+          for (int nb2 = 0; nb2 < DSL / 16; ++nb2) {
+            uint32_t kb[4];
+            ldsm_x4_t(kb, sK + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + sl * DSL + nb2 * 16 + (lane >> 4) * 8);
+            mma16816(dq[2 * nb2], a, kb[0], kb[1]);
+            mma16816(dq[2 * nb2 + 1], a, kb[2], kb[3]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int qi = q0 + qb_i * 16 + (lane >> 2) + r * 8;
+          if (qi < p.sq) {
+            float* dst = p.dq_accum + ((static_cast<long long>(b) * p.sq + qi) * p.hq + h) * DH + sl * DSL;
+#pragma unroll
+            for (int i = 0; i < DSL / 8; ++i) {
+              atomicAdd(dst + i * 8 + 2 * (lane & 3), dq[i][2 * r]);
+              atomicAdd(dst + i * 8 + 2 * (lane & 3) + 1, dq[i][2 * r + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // write dK, dV (bf16)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = k0 + warp * 16 + (lane >> 2) + r * 8;
+    if (key < p.sk) {
+      bf16* dkr = p.dk + (static_cast<long long>(b) * p.sk + key) * p.lddk + hk * DH;
+      bf16* dvr = p.dv + (static_cast<long long>(b) * p.sk + key) * p.lddv + hk * DH;
+#pragma unroll
+      for (int i = 0; i < DH / 8; ++i) {
+        *reinterpret_cast<uint32_t*>(dkr + i * 8 + 2 * (lane & 3)) = pack_bf16x2(dk[i][2 * r], dk[i][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(dvr + i * 8 + 2 * (lane & 3)) = pack_bf16x2(dv[i][2 * r], dv[i][2 * r + 1]);
+      }
+    }
+  }
+}
+
+// dq_accum f32 [B,Sq,Hq,DH] -> dq bf16 with row stride lddq
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq, long long rows, int width) {
+  const int vpr = width / 4;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = rows * vpr;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long r = i / vpr;
+    const int c = static_cast<int>(i % vpr) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(acc + r * width + c);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dq + r * lddq + c) = pk;
+  }
+}
+
+static int fill_params(const slam_attn_args* a, AttnP& p, bool bwd) {
+  SLAM_CHECK_ARG(a != nullptr, "attn: null args");
+  SLAM_CHECK_ARG(a->dh == 64 || a->dh == 128, "attn: dh must be 64 or 128 (got %d)", a->dh);
+  SLAM_CHECK_ARG(a->hkv > 0 && a->hq % a->hkv == 0, "attn: hq %% hkv != 0");
+  SLAM_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "attn: row strides must be multiples of 8");
+  SLAM_CHECK_ARG(!a->causal || a->sq == a->sk, "attn: causal requires sq == sk");
+  p.q = reinterpret_cast<const bf16*>(a->q); p.ldq = a->ldq;
+  p.k = reinterpret_cast<const bf16*>(a->k); p.ldk = a->ldk;
+  p.v = reinterpret_cast<const bf16*>(a->v); p.ldv = a->ldv;
+  p.out = reinterpret_cast<bf16*>(a->out); p.ldo = a->ldo;
+  p.lse = a->lse;
+  p.key_mask = a->key_mask;
+  p.batch = a->batch; p.sq = a->sq; p.sk = a->sk; p.hq = a->hq; p.hkv = a->hkv;
+  p.causal = a->causal;
+  p.scale = a->scale;
+  p.dout = reinterpret_cast<const bf16*>(a->dout); p.lddo = a->lddo;
+  p.dq = reinterpret_cast<bf16*>(a->dq); p.lddq = a->lddq;
+  p.dk = reinterpret_cast<bf16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<bf16*>(a->dv); p.lddv = a->lddv;
+  p.delta = a->delta;
+  p.dq_accum = a->dq_accum;
+  if (bwd) {
+    SLAM_CHECK_ARG(a->lse && a->delta && a->dq_accum && a->dout && a->dq && a->dk && a->dv, "attn_bwd: missing buffers");
+    SLAM_CHECK_ARG(a->lddo % 8 == 0 && a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0, "attn_bwd: row strides must be multiples of 8");
+  }
+  return 0;
+}
+
+template <int DH>
+static int launch_fwd(const AttnP& p, cudaStream_t st) {
+  constexpr int SMEM = 3 * 64 * (DH + 8) * 2;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    set = true;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div(p.sq, 64)), p.hq, p.batch);
+  attn_fwd_kernel<DH><<<grid, 128, SMEM, st>>>(p);
+  SLAM_LAUNCH_CHECK("slam_attn_fwd");
+  return 0;
+}
+template <int DH, int BQ>
+static int launch_bwd(const AttnP& p, cudaStream_t st) {
+  constexpr int SMEM = (2 * 64 + 2 * BQ) * (DH + 8) * 2 + 64 * (BQ + 8) * 2 + 2 * BQ * 4;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(attn_bwd_kernel<DH, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    set = true;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div(p.sk, 64)), p.hkv, p.batch);
+  attn_bwd_kernel<DH, BQ><<<grid, 128, SMEM, st>>>(p);
+  SLAM_LAUNCH_CHECK("slam_attn_bwd");
+  return 0;
+}
+
+}  // namespace slam
+
+extern "C" int slam_attn_fwd(const slam_attn_args* a, void* stream) {
+  using namespace slam;
+  AttnP p;
+  int rc = fill_params(a, p, false);
+  if (rc != 0) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return a->dh == 64 ? launch_fwd<64>(p, st) : launch_fwd<128>(p, st);
+}
+
+extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
+  using namespace slam;
+  AttnP p;
+  int rc = fill_params(a, p, true);
+  if (rc != 0) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = static_cast<long long>(p.batch) * p.sq;
+  const int width = p.hq * a->dh;
+  cudaError_t e = cudaMemsetAsync(p.dq_accum, 0, static_cast<size_t>(rows) * width * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("attn_bwd: memset failed: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  const int total_warps = p.batch * p.sq * p.hq;
+  attn_delta_kernel<<<static_cast<unsigned>(ceil_div(total_warps, 8)), 256, 0, st>>>(p, a->dh);
+  SLAM_LAUNCH_CHECK("slam_attn_bwd.delta");
+  rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
+  if (rc != 0) return rc;
+  SLAM_CHECK_ARG(p.lddq >= width || p.hq * a->dh <= p.lddq, "attn_bwd: lddq too small");
+  const long long nvec = rows * (width / 4);
+  long long blocks = ceil_div(nvec, 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  attn_dq_convert_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p.dq_accum, p.dq, p.lddq, rows, width);
+  SLAM_LAUNCH_CHECK("slam_attn_bwd.convert");
+  return 0;
+}
