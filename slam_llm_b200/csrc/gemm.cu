@@ -329,24 +329,14 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
 
 static int pick_block_n(int m, int n) {
   if (n <= 64) return 64;
+  if (n < 256) return 128;
+  // measured on B200 (profiles/r01_gemm_bench_v0.json): BLOCK_N=128 tiles are shared-memory-bandwidth bound
+  // (~0.65x the per-flop rate of 256), so 256 wins even when it costs an extra partial wave.
   const int sms = num_sms();
   const int64_t mt = ceil_div(m, GEMM_BM);
-  double best = 1e30;
-  int best_bn = 128;
-  const int cands[2] = {256, 128};
-  for (int i = 0; i < 2; ++i) {
-    const int bn = cands[i];
-    if (bn == 256 && n < 256) continue;
-    const int64_t tiles = mt * ceil_div(n, bn);
-    const int64_t waves = ceil_div(tiles, sms);
-    // BLOCK_N=128 tiles are shared-memory-bandwidth limited (A re-read per 128 columns): ~12% slower per flop
-    const double cost = static_cast<double>(waves) * bn * (bn == 128 ? 1.12 : 1.0);
-    if (cost < best) {
-      best = cost;
-      best_bn = bn;
-    }
-  }
-  return best_bn;
+  const double c256 = static_cast<double>(ceil_div(mt * ceil_div(n, 256), sms)) * 256.0;
+  const double c128 = static_cast<double>(ceil_div(mt * ceil_div(n, 128), sms)) * 128.0 * 1.5;
+  return c128 < c256 ? 128 : 256;
 }
 
 }  // namespace slam

@@ -1,0 +1,610 @@
+"""The SLAM-LLM training step on B200: Whisper encoder -> projector -> merge -> Llama(+LoRA) -> CE,
+backward through projector/LoRA only, flat-buffer AdamW — every FLOP in libslam_b200.so kernels.
+
+Mirrors (file:line under /root/reference):
+  encoder      src/slam_llm/models/encoder.py:13-30 (+ openai-whisper AudioEncoder modules)
+  projector    src/slam_llm/models/projector.py:5-27
+  merge        src/slam_llm/models/slam_model.py:370-392
+  decoder      transformers LlamaForCausalLM + peft LoRA, called at src/slam_llm/models/slam_model.py:400
+  loss / acc   HF loss block + src/slam_llm/utils/metric.py:3-20 (slam_model.py:402-405)
+  optimizer    src/slam_llm/pipeline/finetune.py:247-251
+
+Data layout in HBM (180 GB/GPU): frozen weights live in bf16 twice — W [out,in] for the forward GEMM and
+W^T [in,out] for the dgrad GEMM — so every GEMM is the same K-major tcgen05 kernel with TMA-loaded operands.
+All trainables (projector + LoRA) live in ONE flat fp32 arena (param / grad / exp_avg / exp_avg_sq) so the
+data-parallel exchange is one NCCL all-reduce and the optimizer is one kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .config import ATTN_LINEARS, MLP_LINEARS, EncoderCfg, LlmCfg, LoraCfg, ProjCfg, linear_shape
+from .frontend import mel_filterbank, sinusoids
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("slam_llm_b200 engine needs a CUDA (B200) device; there is no CPU fallback")
+    return device
+
+
+# =====================================================================================================
+# flat arena of trainables
+# =====================================================================================================
+class TrainableArena:
+    """One flat fp32 buffer each for parameters, gradients and the two Adam moments."""
+
+    def __init__(self) -> None:
+        self._specs: List[Tuple[str, Tuple[int, ...]]] = []
+        self._offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self.n = 0
+        self.param = self.grad = self.exp_avg = self.exp_avg_sq = None
+        self.step_count = 0
+
+    def add(self, name: str, shape: Tuple[int, ...]) -> None:
+        assert self.param is None and name not in self._offsets
+        numel = int(math.prod(shape))
+        self._offsets[name] = (self.n, tuple(shape))
+        self.n += _round_up(numel, 8)  # keep every tensor 32-byte aligned for vector kernels
+
+    def finalize(self, device) -> None:
+        self.param = torch.zeros(self.n, device=device, dtype=F32)
+        self.grad = torch.zeros(self.n, device=device, dtype=F32)
+        self.exp_avg = torch.zeros(self.n, device=device, dtype=F32)
+        self.exp_avg_sq = torch.zeros(self.n, device=device, dtype=F32)
+
+    def names(self) -> List[str]:
+        return list(self._offsets)
+
+    def offset(self, name: str) -> int:
+        return self._offsets[name][0]
+
+    def view(self, name: str, which: str = "param") -> torch.Tensor:
+        off, shape = self._offsets[name]
+        return getattr(self, which)[off: off + int(math.prod(shape))].view(shape)
+
+    def adamw_step(self, lr: float, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, grad_div: float = 1.0) -> None:
+        self.step_count += 1
+        ops.adamw_(self.param, self.grad, self.exp_avg, self.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                   weight_decay=weight_decay, step=self.step_count, grad_div=grad_div)
+
+
+# =====================================================================================================
+# Whisper encoder (frozen, forward only)
+# =====================================================================================================
+class WhisperEncoderB200:
+    def __init__(self, cfg: EncoderCfg, weights: Optional[Dict[str, torch.Tensor]], device, seed: int = 42, std: float = 0.02):
+        self.cfg = cfg
+        self.device = _require_cuda(device)
+        d = cfg.d
+        self.k1 = _round_up(3 * cfg.n_mels, 64)
+        if weights is None:
+            weights = self._random(cfg, seed, std)
+        dev = self.device
+
+        def g(name):
+            return weights[name].to(dev, F32)
+
+        w1 = torch.zeros(d, self.k1, device=dev, dtype=F32)
+        w1[:, : 3 * cfg.n_mels] = g("conv1.weight").permute(0, 2, 1).reshape(d, 3 * cfg.n_mels)  # [d, (kk, c)]
+        self.conv1_w, self.conv1_b = w1.to(BF16), g("conv1.bias").contiguous()
+        self.conv2_w = g("conv2.weight").permute(0, 2, 1).reshape(d, 3 * d).to(BF16).contiguous()
+        self.conv2_b = g("conv2.bias").contiguous()
+        self.pos = g("positional_embedding").contiguous()
+        self.layers = []
+        for i in range(cfg.layers):
+            p = f"blocks.{i}."
+            wqkv = torch.cat([g(p + "attn.query.weight"), g(p + "attn.key.weight"), g(p + "attn.value.weight")], 0).to(BF16).contiguous()
+            bqkv = torch.cat([g(p + "attn.query.bias"), torch.zeros(d, device=dev), g(p + "attn.value.bias")]).contiguous()
+            self.layers.append(dict(
+                ln1_w=g(p + "attn_ln.weight").contiguous(), ln1_b=g(p + "attn_ln.bias").contiguous(), wqkv=wqkv, bqkv=bqkv,
+                wo=g(p + "attn.out.weight").to(BF16).contiguous(), bo=g(p + "attn.out.bias").contiguous(),
+                ln2_w=g(p + "mlp_ln.weight").contiguous(), ln2_b=g(p + "mlp_ln.bias").contiguous(),
+                w1=g(p + "mlp.0.weight").to(BF16).contiguous(), b1=g(p + "mlp.0.bias").contiguous(),
+                w2=g(p + "mlp.2.weight").to(BF16).contiguous(), b2=g(p + "mlp.2.bias").contiguous()))
+        self.lnp_w, self.lnp_b = g("ln_post.weight").contiguous(), g("ln_post.bias").contiguous()
+
+    @staticmethod
+    def _random(cfg: EncoderCfg, seed: int, std: float) -> Dict[str, torch.Tensor]:
+        """Random-init AudioEncoder weights generated directly on the device (bench / smoke: no checkpoints offline)."""
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        d = cfg.d
+
+        def n(*s):
+            return torch.randn(*s, generator=g, device="cuda") * std
+
+        w = {"conv1.weight": n(d, cfg.n_mels, 3) * 3, "conv1.bias": n(d), "conv2.weight": n(d, d, 3), "conv2.bias": n(d),
+             "positional_embedding": sinusoids(cfg.n_ctx, d), "ln_post.weight": 1 + n(d), "ln_post.bias": n(d)}
+        for i in range(cfg.layers):
+            p = f"blocks.{i}."
+            w.update({p + "attn.query.weight": n(d, d), p + "attn.query.bias": n(d), p + "attn.key.weight": n(d, d),
+                      p + "attn.value.weight": n(d, d), p + "attn.value.bias": n(d), p + "attn.out.weight": n(d, d), p + "attn.out.bias": n(d),
+                      p + "attn_ln.weight": 1 + n(d), p + "attn_ln.bias": n(d), p + "mlp.0.weight": n(4 * d, d), p + "mlp.0.bias": n(4 * d),
+                      p + "mlp.2.weight": n(d, 4 * d), p + "mlp.2.bias": n(d), p + "mlp_ln.weight": 1 + n(d), p + "mlp_ln.bias": n(d)})
+        return w
+
+    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel f32 [B, T, n_mels] (time-major) -> bf16 [B, ceil(T/2), d]."""
+        cfg = self.cfg
+        B, T, _ = mel.shape
+        d, H = cfg.d, cfg.heads
+        dh = d // H
+        col1 = ops.conv_im2col(mel.contiguous(), 1, self.k1)
+        x1 = ops.gemm(col1, self.conv1_w, bias=self.conv1_b, act=1)                       # GELU(conv1)
+        col2 = ops.conv_im2col(x1.view(B, T, d), 2, 3 * d)
+        Tp = (T + 1) // 2
+        if Tp > self.pos.shape[0]:
+            raise ValueError(f"audio too long for positional_embedding: {Tp} > {self.pos.shape[0]}")
+        x = ops.gemm(col2, self.conv2_w, bias=self.conv2_b, act=1)                        # GELU(conv2), [B*Tp, d]
+        ops.add_pos_(x.view(B, Tp, d), self.pos)
+        M = B * Tp
+        scale = dh ** -0.5                                                                 # (q dh^-.25)(k dh^-.25)
+        for L in self.layers:
+            h = ops.layernorm(x, L["ln1_w"], L["ln1_b"])
+            qkv = ops.gemm(h, L["wqkv"], bias=L["bqkv"])
+            q = qkv[:, :d].view(B, Tp, H, dh)
+            k = qkv[:, d:2 * d].view(B, Tp, H, dh)
+            v = qkv[:, 2 * d:].view(B, Tp, H, dh)
+            a, _ = ops.attn_fwd(q, k, v, causal=False, scale=scale)                        # no mask on padded frames (ref Q9)
+            ops.gemm(a.view(M, d), L["wo"], bias=L["bo"], residual=x, out=x)
+            h = ops.layernorm(x, L["ln2_w"], L["ln2_b"])
+            f = ops.gemm(h, L["w1"], bias=L["b1"], act=1)
+            ops.gemm(f, L["w2"], bias=L["b2"], residual=x, out=x)
+        return ops.layernorm(x, self.lnp_w, self.lnp_b).view(B, Tp, d)
+
+
+# =====================================================================================================
+# projector (trainable): EncoderProjectorConcat
+# =====================================================================================================
+class ProjectorB200:
+    PREFIX = "encoder_projector."
+
+    def __init__(self, enc: EncoderCfg, llm: LlmCfg, proj: ProjCfg, arena: TrainableArena):
+        if proj.kind != "linear":
+            raise NotImplementedError(f"projector kind {proj.kind!r}: only the concat-linear projector is on the B200 path so far")
+        self.cfg, self.k, self.d_in, self.hidden, self.d_out = proj, proj.k, enc.d * proj.k, proj.hidden, llm.d
+        self.arena = arena
+        arena.add(self.PREFIX + "linear1.weight", (self.hidden, self.d_in))
+        arena.add(self.PREFIX + "linear1.bias", (self.hidden,))
+        arena.add(self.PREFIX + "linear2.weight", (self.d_out, self.hidden))
+        arena.add(self.PREFIX + "linear2.bias", (self.d_out,))
+        self.saved = None
+
+    def init_weights(self, weights: Optional[Dict[str, torch.Tensor]], seed: int = 45) -> None:
+        a = self.arena
+        if weights is not None:
+            for k in ("linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"):
+                a.view(self.PREFIX + k).copy_(weights[k].to(a.param.device, F32))
+            return
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for name, fan_in in (("linear1", self.d_in), ("linear2", self.hidden)):
+            b = 1.0 / math.sqrt(fan_in)
+            for suffix in ("weight", "bias"):
+                v = a.view(self.PREFIX + f"{name}.{suffix}")
+                v.copy_((torch.rand(v.shape, generator=g, device="cuda") * 2 - 1) * b)
+
+    def forward(self, enc_out: torch.Tensor, save: bool) -> torch.Tensor:
+        """enc_out bf16 [B, T', d] -> bf16 [B, T'//k, D]."""
+        B, Tp, d = enc_out.shape
+        Ta = Tp // self.k
+        if Tp % self.k:
+            enc_out = enc_out[:, : Ta * self.k].contiguous()                              # projector.py:17-19 (drop tail frames)
+        xcat = enc_out.reshape(B * Ta, self.k * d)
+        a = self.arena
+        w1 = ops.cast_bf16(a.view(self.PREFIX + "linear1.weight"))
+        w2 = ops.cast_bf16(a.view(self.PREFIX + "linear2.weight"))
+        h1 = ops.gemm(xcat, w1, bias=a.view(self.PREFIX + "linear1.bias"), act=2)
+        y = ops.gemm(h1, w2, bias=a.view(self.PREFIX + "linear2.bias"))
+        if save:
+            self.saved = (xcat, h1, w2)
+        return y.view(B, Ta, self.d_out)
+
+    def backward(self, dy: torch.Tensor) -> None:
+        """dy bf16 [B, Ta, D]; writes grads of linear1/linear2 into the arena (encoder frozen: no dX)."""
+        xcat, h1, w2 = self.saved
+        self.saved = None
+        a = self.arena
+        M = xcat.shape[0]
+        dy2 = dy.reshape(M, self.d_out)
+        Mp = _round_up(M, 8)
+
+        def tpose(x):  # [M, C] -> [C, M] with a 16-byte aligned leading dimension
+            buf = torch.zeros((x.shape[1], Mp), device=x.device, dtype=BF16) if Mp != M else torch.empty((x.shape[1], M), device=x.device, dtype=BF16)
+            return ops.transpose(x, out=buf[:, :M])
+
+        dyT, h1T = tpose(dy2), tpose(h1)
+        ops.gemm(dyT, h1T, out=a.view(self.PREFIX + "linear2.weight", "grad"), out_f32=True)          # dW2 = dY^T H1
+        ops.colsum(dy2, a.view(self.PREFIX + "linear2.bias", "grad"))
+        w2T = ops.transpose(w2)                                                                          # [hidden, D]
+        dh1 = ops.gemm(dy2, w2T)                                                                         # dH1 = dY W2
+        dh1 = ops.relu_bwd(dh1, h1, out=dh1)
+        ops.gemm(tpose(dh1), tpose(xcat), out=a.view(self.PREFIX + "linear1.weight", "grad"), out_f32=True)  # dW1 = dH1^T X
+        ops.colsum(dh1, a.view(self.PREFIX + "linear1.bias", "grad"))
+
+
+# =====================================================================================================
+# Llama decoder with frozen base weights + LoRA adapters
+# =====================================================================================================
+GROUPS = {"qkv": ("q_proj", "k_proj", "v_proj"), "o": ("o_proj",), "gu": ("gate_proj", "up_proj"), "down": ("down_proj",)}
+
+
+class LlamaLoRAB200:
+    LORA_PREFIX = "llm.base_model.model."
+
+    def __init__(self, cfg: LlmCfg, lora: Optional[LoraCfg], arena: TrainableArena, device, weights: Optional[Dict[str, torch.Tensor]] = None,
+                 seed: int = 43, std: float = 0.02):
+        self.cfg, self.lora, self.arena = cfg, lora, arena
+        self.device = _require_cuda(device)
+        dev = self.device
+        L = cfg.layers
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+
+        def base(name: str, shape) -> torch.Tensor:
+            if weights is not None:
+                return weights[name].to(dev, BF16).contiguous()
+            return (torch.randn(*shape, generator=gen, device=dev, dtype=F32) * std).to(BF16)
+
+        def norm_w(name: str) -> torch.Tensor:
+            if weights is not None:
+                return weights[name].to(dev, BF16).contiguous()
+            return (1.0 + torch.randn(cfg.d, generator=gen, device=dev) * std).to(BF16)
+
+        self.embed = base("model.embed_tokens.weight", (cfg.vocab, cfg.d))
+        self.layers = []
+        for i in range(L):
+            p = f"model.layers.{i}."
+            q, k, v = (base(p + f"self_attn.{n}.weight", linear_shape(cfg, n)) for n in ("q_proj", "k_proj", "v_proj"))
+            wqkv = torch.cat([q, k, v], 0).contiguous()
+            del q, k, v
+            wo = base(p + "self_attn.o_proj.weight", linear_shape(cfg, "o_proj"))
+            g_, u_ = (base(p + f"mlp.{n}.weight", linear_shape(cfg, n)) for n in ("gate_proj", "up_proj"))
+            wgu = torch.cat([g_, u_], 0).contiguous()
+            del g_, u_
+            wd = base(p + "mlp.down_proj.weight", linear_shape(cfg, "down_proj"))
+            self.layers.append(dict(wqkv=wqkv, wqkvT=ops.transpose(wqkv), wo=wo, woT=ops.transpose(wo), wgu=wgu, wguT=ops.transpose(wgu),
+                                    wd=wd, wdT=ops.transpose(wd), ln1=norm_w(p + "input_layernorm.weight"),
+                                    ln2=norm_w(p + "post_attention_layernorm.weight")))
+        self.norm = norm_w("model.norm.weight")
+        self.lm_head = base("lm_head.weight", (cfg.vocab, cfg.d))
+        self.lm_headT = ops.transpose(self.lm_head)
+        self._rope_cache: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+        # ---- LoRA bookkeeping: per fused-GEMM group, rank-padded packed operands for all layers
+        self.groups: Dict[str, dict] = {}
+        if lora is not None:
+            for gname, members in GROUPS.items():
+                tg = [m for m in members if m in lora.targets]
+                if not tg:
+                    continue
+                in_f = linear_shape(cfg, members[0])[1]
+                col, cols = 0, {}
+                for m in members:
+                    cols[m] = col
+                    col += linear_shape(cfg, m)[0]
+                out_total = col
+                rpad = _round_up(len(tg) * lora.r, 64)
+                info = dict(targets=tg, in_f=in_f, out_total=out_total, rpad=rpad, cols=cols,
+                            roff={m: j * lora.r for j, m in enumerate(tg)},
+                            a_cat=torch.zeros(L, rpad, in_f, device=dev, dtype=BF16), a_catT=torch.zeros(L, in_f, rpad, device=dev, dtype=BF16),
+                            b_cat=torch.zeros(L, out_total, rpad, device=dev, dtype=BF16), b_catT=torch.zeros(L, rpad, out_total, device=dev, dtype=BF16))
+                self.groups[gname] = info
+                for m in tg:
+                    out_f = linear_shape(cfg, m)[0]
+                    arena.add(self._pname(m, "A"), (L, lora.r, in_f))      # lora_A.weight [r, in] stacked over layers
+                    arena.add(self._pname(m, "Bt"), (L, lora.r, out_f))    # lora_B.weight^T [r, out] stacked over layers
+        self.saved: Optional[dict] = None
+
+    # names of the stacked arena tensors (the slam_llm mirror exposes them under the peft key names)
+    @staticmethod
+    def _pname(target: str, which: str) -> str:
+        return f"lora.{target}.{which}"
+
+    def init_lora(self, weights: Optional[Dict[str, torch.Tensor]], seed: int = 44, b_std: float = 0.0) -> None:
+        """weights: peft-named dict ('model.layers.i.self_attn.q_proj.lora_A.default.weight').  Without weights:
+        A ~ kaiming_uniform(a=sqrt(5)), B = 0 (peft reset_lora_parameters) or N(0, b_std) when b_std > 0."""
+        if self.lora is None:
+            return
+        cfg, lora, a = self.cfg, self.lora, self.arena
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for m in lora.targets:
+            out_f, in_f = linear_shape(cfg, m)
+            mod = "self_attn" if m in ATTN_LINEARS else "mlp"
+            A, Bt = a.view(self._pname(m, "A")), a.view(self._pname(m, "Bt"))
+            for i in range(cfg.layers):
+                if weights is not None:
+                    p = f"model.layers.{i}.{mod}.{m}."
+                    A[i].copy_(weights[p + "lora_A.default.weight"].to(A.device, F32))
+                    Bt[i].copy_(weights[p + "lora_B.default.weight"].to(A.device, F32).t())
+                else:
+                    A[i].copy_((torch.rand(lora.r, in_f, generator=g, device="cuda") * 2 - 1) / math.sqrt(in_f))
+                    if b_std > 0:
+                        Bt[i].copy_(torch.randn(out_f, lora.r, generator=g, device="cuda").t() * b_std)
+                    else:
+                        Bt[i].zero_()
+
+    def lora_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
+        """peft-0.6-named views (lora_B as a transposed view of the stacked [r,out] storage)."""
+        out = {}
+        if self.lora is None:
+            return out
+        for m in self.lora.targets:
+            mod = "self_attn" if m in ATTN_LINEARS else "mlp"
+            A, Bt = self.arena.view(self._pname(m, "A"), which), self.arena.view(self._pname(m, "Bt"), which)
+            for i in range(self.cfg.layers):
+                p = f"{self.LORA_PREFIX}model.layers.{i}.{mod}.{m}."
+                out[p + "lora_A.default.weight"] = A[i]
+                out[p + "lora_B.default.weight"] = Bt[i].t()
+        return out
+
+    def pack_lora(self) -> None:
+        """fp32 adapters -> rank-padded bf16 GEMM operands for all layers (8 launches per target, once per step)."""
+        if self.lora is None:
+            return
+        L, r, s = self.cfg.layers, self.lora.r, self.lora.scaling
+        for info in self.groups.values():
+            in_f, out_total, rpad = info["in_f"], info["out_total"], info["rpad"]
+            for m in info["targets"]:
+                out_f = linear_shape(self.cfg, m)[0]
+                off, col = info["roff"][m], info["cols"][m]
+                A, Bt = self.arena.view(self._pname(m, "A")), self.arena.view(self._pname(m, "Bt"))
+                ops.pack2d(A, info["a_cat"], batch=L, rows=r, cols=in_f, src_bs=r * in_f, src_ld=in_f, dst_bs=rpad * in_f, dst_ld=in_f,
+                           dst_off=off * in_f)
+                ops.pack2d(A, info["a_catT"], batch=L, rows=r, cols=in_f, src_bs=r * in_f, src_ld=in_f, dst_bs=in_f * rpad, dst_ld=rpad,
+                           dst_off=off, transpose=True)
+                ops.pack2d(Bt, info["b_catT"], batch=L, rows=r, cols=out_f, src_bs=r * out_f, src_ld=out_f, dst_bs=rpad * out_total,
+                           dst_ld=out_total, dst_off=off * out_total + col, scale=s)
+                ops.pack2d(Bt, info["b_cat"], batch=L, rows=r, cols=out_f, src_bs=r * out_f, src_ld=out_f, dst_bs=out_total * rpad, dst_ld=rpad,
+                           dst_off=col * rpad + off, scale=s, transpose=True)
+
+    def rope_tables(self, S: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if S not in self._rope_cache:
+            dh = self.cfg.dh
+            inv = 1.0 / (self.cfg.rope_theta ** (torch.arange(0, dh, 2, dtype=F32, device=self.device) / dh))
+            fr = torch.outer(torch.arange(S, dtype=F32, device=self.device), inv)
+            self._rope_cache[S] = (fr.cos().contiguous(), fr.sin().contiguous())
+        return self._rope_cache[S]
+
+    # ---------------------------------------------------------------------------------------- linear (+LoRA) helpers
+    def _lin_fwd(self, x, w, gname: str, li: int, residual=None, out=None):
+        info = self.groups.get(gname)
+        if info is None:
+            return ops.gemm(x, w, residual=residual, out=out), None
+        t = ops.gemm(x, info["a_cat"][li])                                                 # T = x A_cat^T  [M, rpad]
+        return ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out), t   # fused base + LoRA tile
+
+    def _lin_bwd(self, dy, wT, gname: str, li: int, x_in, t):
+        """dX = dY W + (dY B_s) A  and LoRA grads (dA = U^T x, dB^T = s T^T dY) into the arena."""
+        info = self.groups.get(gname)
+        if info is None:
+            return ops.gemm(dy, wT)
+        u = ops.gemm(dy, info["b_catT"][li])                                               # U = dY (s B)  [M, rpad]
+        dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li])
+        r, s = self.lora.r, self.lora.scaling
+        for m in info["targets"]:
+            off, col = info["roff"][m], info["cols"][m]
+            out_f = linear_shape(self.cfg, m)[0]
+            gA = self.arena.view(self._pname(m, "A"), "grad")[li]
+            gBt = self.arena.view(self._pname(m, "Bt"), "grad")[li]
+            ops.wgrad_thin(u[:, off: off + r], x_in, gA)
+            ops.wgrad_thin(t[:, off: off + r], dy[:, col: col + out_f], gBt, scale=s)
+        return dx
+
+    # ---------------------------------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor, key_mask: torch.Tensor, save: bool) -> torch.Tensor:
+        """x bf16 [B,S,D] (inputs_embeds), key_mask u8 [B,S] -> final normed hidden bf16 [B*S, D]."""
+        cfg = self.cfg
+        B, S, D = x.shape
+        M = B * S
+        H, Hkv, dh, Dq, Dkv = cfg.heads, cfg.kv_heads, cfg.dh, cfg.dq, cfg.dkv
+        cos, sin = self.rope_tables(S)
+        scale = 1.0 / math.sqrt(dh)
+        x = x.reshape(M, D)
+        saved_layers = []
+        for li, Lw in enumerate(self.layers):
+            xn1, rstd1 = ops.rmsnorm_fwd(x, Lw["ln1"], cfg.eps, need_rstd=save)
+            qkv, t_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li)
+            ops.rope_(qkv[:, :Dq], H, dh, S, cos, sin)
+            ops.rope_(qkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin)
+            q = qkv[:, :Dq].view(B, S, H, dh)
+            k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
+            v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
+            attn, lse = ops.attn_fwd(q, k, v, causal=True, scale=scale, key_mask=key_mask, need_lse=save)
+            attn2 = attn.view(M, Dq)
+            x2, t_o = self._lin_fwd(attn2, Lw["wo"], "o", li, residual=x)
+            xn2, rstd2 = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=save)
+            gu, t_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
+            hmid = ops.swiglu_fwd(gu)
+            x3, t_d = self._lin_fwd(hmid, Lw["wd"], "down", li, residual=x2)
+            if save:
+                keep = dict(x=x, rstd1=rstd1, qkv=qkv, attn=attn, lse=lse, x2=x2, rstd2=rstd2, gu=gu)
+                if "qkv" in self.groups:
+                    keep.update(xn1=xn1, t_qkv=t_qkv)
+                if "o" in self.groups:
+                    keep.update(t_o=t_o)
+                if "gu" in self.groups:
+                    keep.update(xn2=xn2, t_gu=t_gu)
+                if "down" in self.groups:
+                    keep.update(hmid=hmid, t_d=t_d)
+                saved_layers.append(keep)
+            x = x3
+        xf, rstd_f = ops.rmsnorm_fwd(x, self.norm, cfg.eps, need_rstd=save)
+        if save:
+            self.saved = dict(layers=saved_layers, x_last=x, rstd_f=rstd_f, B=B, S=S, key_mask=key_mask)
+        return xf
+
+    # ---------------------------------------------------------------------------------------- backward
+    def backward(self, dxf: torch.Tensor) -> torch.Tensor:
+        """dxf bf16 [B*S, D]: grad wrt the final normed hidden -> grad wrt inputs_embeds bf16 [B,S,D]."""
+        cfg, sv = self.cfg, self.saved
+        self.saved = None
+        B, S = sv["B"], sv["S"]
+        M = B * S
+        H, Hkv, dh, Dq, Dkv = cfg.heads, cfg.kv_heads, cfg.dh, cfg.dq, cfg.dkv
+        cos, sin = self.rope_tables(S)
+        scale = 1.0 / math.sqrt(dh)
+        dx = ops.rmsnorm_bwd(dxf, sv["x_last"], self.norm, sv["rstd_f"])
+        for li in range(cfg.layers - 1, -1, -1):
+            Lw, kp = self.layers[li], sv["layers"][li]
+            # ---- MLP block: x3 = x2 + down(silu(g) * u)
+            dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp.get("hmid"), kp.get("t_d"))
+            dgu = ops.swiglu_bwd(kp["gu"], dhmid)
+            dxn2 = self._lin_bwd(dgu, Lw["wguT"], "gu", li, kp.get("xn2"), kp.get("t_gu"))
+            dx2 = ops.rmsnorm_bwd(dxn2, kp["x2"], Lw["ln2"], kp["rstd2"], dres=dx)
+            # ---- attention block: x2 = x + o(attn(rope(qkv(norm(x)))))
+            dattn = self._lin_bwd(dx2, Lw["woT"], "o", li, kp["attn"].view(M, Dq), kp.get("t_o"))
+            qkv = kp["qkv"]
+            q = qkv[:, :Dq].view(B, S, H, dh)
+            k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
+            v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
+            dqkv = torch.empty_like(qkv)
+            ops.attn_bwd(q, k, v, kp["attn"], kp["lse"], dattn.view(B, S, H, dh), causal=True, scale=scale, key_mask=sv["key_mask"],
+                         dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh))
+            ops.rope_(dqkv[:, :Dq], H, dh, S, cos, sin, inverse=True)
+            ops.rope_(dqkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin, inverse=True)
+            dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp.get("xn1"), kp.get("t_qkv"))
+            dx = ops.rmsnorm_bwd(dxn1, kp["x"], Lw["ln1"], kp["rstd1"], dres=dx2)
+            sv["layers"][li] = None
+        return dx.view(B, S, cfg.d)
+
+
+# =====================================================================================================
+# the step
+# =====================================================================================================
+class SlamStepB200:
+    """log-mel -> encoder -> projector -> merge -> decoder -> CE (+acc); backward; AdamW."""
+
+    def __init__(self, enc_cfg: EncoderCfg, llm_cfg: LlmCfg, lora_cfg: Optional[LoraCfg], proj_cfg: ProjCfg, device="cuda:0",
+                 enc_weights=None, llm_weights=None, lora_weights=None, proj_weights=None, seed: int = 42, lora_b_std: float = 0.0):
+        self.device = _require_cuda(device)
+        torch.cuda.set_device(self.device)
+        self.enc_cfg, self.llm_cfg, self.lora_cfg, self.proj_cfg = enc_cfg, llm_cfg, lora_cfg, proj_cfg
+        self.arena = TrainableArena()
+        self.encoder = WhisperEncoderB200(enc_cfg, enc_weights, self.device, seed=seed)
+        self.projector = ProjectorB200(enc_cfg, llm_cfg, proj_cfg, self.arena)
+        self.llm = LlamaLoRAB200(llm_cfg, lora_cfg, self.arena, self.device, llm_weights, seed=seed + 1)
+        self.arena.finalize(self.device)
+        self.projector.init_weights(proj_weights, seed=seed + 3)
+        self.llm.init_lora(lora_weights, seed=seed + 2, b_std=lora_b_std)
+        self.filters_t = mel_filterbank(enc_cfg.n_mels).t().contiguous().to(self.device)
+        self._stats = None
+        self._ctx = None
+
+    # ------------------------------------------------------------------ state dict in the reference's key names
+    def trainable_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
+        out = {n: self.arena.view(n, which) for n in self.arena.names() if n.startswith(ProjectorB200.PREFIX)}
+        out.update(self.llm.lora_state(which))
+        return out
+
+    def load_trainable_state(self, sd: Dict[str, torch.Tensor]) -> List[str]:
+        mine = self.trainable_state()
+        loaded = []
+        for k, v in sd.items():
+            if k in mine:
+                mine[k].copy_(v.to(self.device, F32))
+                loaded.append(k)
+        return loaded
+
+    # ------------------------------------------------------------------ front end
+    def log_mel(self, pcm: torch.Tensor) -> torch.Tensor:
+        """pcm f32 [B, n_samples] on device -> [B, n_samples//160, n_mels]."""
+        return ops.logmel(pcm.contiguous(), self.filters_t)
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def label_rows(labels: torch.Tensor, full: bool = False):
+        """Rows (b*S + s) of the hidden states whose NEXT-token label is not -100, and those targets
+        (HF shift: logits[:, :-1] vs labels[:, 1:]).  Works on CPU or GPU tensors; the train loop calls it on the
+        CPU copy before the H2D so no device sync is needed."""
+        B, S = labels.shape
+        tgt = torch.full_like(labels, -100)
+        tgt[:, :-1] = labels[:, 1:]
+        if full:
+            idx = torch.arange(B * S, device=labels.device)
+        else:
+            idx = torch.nonzero(tgt.reshape(-1) != -100).squeeze(1)
+        return idx.to(torch.int32), tgt.reshape(-1)[idx.long()].contiguous()
+
+    def forward(self, batch: Dict[str, torch.Tensor], train: bool = True, full_logits: bool = False):
+        """batch: collator contract (input_ids, labels, attention_mask, modality_mask, audio_mel | audio_pcm) on device.
+        Optional precomputed '_rows' (int32) / '_targets' (int64) avoid a device->host sync.
+        Returns (loss, acc, logits_or_None); loss/acc are 0-dim device tensors."""
+        dev = self.device
+        ids = batch["input_ids"].to(dev).contiguous()
+        labels = batch["labels"].to(dev)
+        key_mask = batch["attention_mask"].to(dev).to(torch.uint8).contiguous()
+        mod_mask = batch["modality_mask"].to(dev).to(torch.uint8).contiguous()
+        mel = batch.get("audio_mel")
+        if mel is None:
+            mel = self.log_mel(batch["audio_pcm"].to(dev, F32))
+        else:
+            mel = mel.to(dev, F32)
+        B, S = ids.shape
+        if train:
+            self.llm.pack_lora()
+        enc_out = self.encoder.forward(mel)
+        aud = self.projector.forward(enc_out, save=train)
+        x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
+        xf = self.llm.forward(x, key_mask, save=train)
+        if "_rows" in batch and not full_logits:
+            rows, tgts = batch["_rows"].to(dev), batch["_targets"].to(dev)
+        else:
+            rows, tgts = self.label_rows(labels, full=full_logits)
+        R = rows.numel()
+        hsel = xf if full_logits else ops.gather_rows(xf, rows)
+        logits = ops.gemm(hsel, self.llm.lm_head, out_f32=True)                            # fp32 logits (HF .float())
+        loss_sum = torch.zeros(1, device=dev, dtype=F32)
+        n_valid = torch.zeros(1, device=dev, dtype=torch.int32)
+        n_correct = torch.zeros(1, device=dev, dtype=torch.int32)
+        ops.cross_entropy(logits, tgts, (loss_sum, n_valid, n_correct))
+        nv = n_valid.to(F32)
+        loss = (loss_sum / nv).squeeze(0)
+        acc = (n_correct.to(F32) / nv).squeeze(0)
+        if train:
+            self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, mod_mask=mod_mask, Ta=aud.shape[1], R=R)
+        return loss, acc, (logits.view(B, S, -1) if full_logits else None)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
+        """Backward of the last forward(train=True); grad_out is d(total)/d(loss) (device scalar, default 1)."""
+        c = self._ctx
+        self._ctx = None
+        dev = self.device
+        gs = (1.0 / c["nv"]) if grad_out is None else (grad_out.to(dev, F32).reshape(1) / c["nv"])
+        gs = gs.contiguous()
+        logits = c["logits"]
+        R, V = logits.shape
+        dlogits = torch.empty((R, V), device=dev, dtype=BF16)
+        scratch = (torch.zeros(1, device=dev), torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, device=dev, dtype=torch.int32))
+        ops.cross_entropy(logits, c["tgts"], scratch, dlogits, gs)
+        dh = ops.gemm(dlogits, self.llm.lm_headT)                                          # [R, D]
+        M = c["B"] * c["S"]
+        if c["full"]:
+            dxf = dh
+        else:
+            dxf = torch.zeros((M, self.llm_cfg.d), device=dev, dtype=BF16)
+            ops.scatter_rows(dh, c["rows"], dxf)
+        dx = self.llm.backward(dxf)
+        daud = ops.embed_merge_bwd(c["mod_mask"], dx.contiguous(), c["Ta"])
+        self.projector.backward(daud)
+
+    def optimizer_step(self, lr: float, weight_decay: float = 0.0, grad_div: float = 1.0) -> None:
+        self.arena.adamw_step(lr, weight_decay, grad_div=grad_div)
+
+    def train_step(self, batch, lr: float = 1e-4, weight_decay: float = 0.0, world_size: int = 1):
+        loss, acc, _ = self.forward(batch, train=True)
+        self.backward()
+        if world_size > 1:
+            torch.distributed.all_reduce(self.arena.grad)                                   # the one data-path collective
+        self.optimizer_step(lr, weight_decay, grad_div=float(world_size))
+        return loss, acc

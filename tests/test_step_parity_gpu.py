@@ -1,0 +1,131 @@
+"""Whole-step parity on the GPU: the B200 engine (through the C ABI) against the CPU oracle on identical
+seeded synthetic inputs and identical weights — mel, encoder hidden states, projector output, loss, accuracy,
+LoRA/projector gradients and the parameters after one AdamW step.
+
+Tolerances (bf16 compute / fp32 accumulate vs fp32 oracle):
+  activations: max|d|/max|ref| <= 2e-2 and cosine >= 0.999;  loss: relative <= 5e-3;
+  gradients:   cosine >= 0.99 and relative L2 <= 3e-2 (per tensor, tensors with non-negligible norm)."""
+import pytest
+import torch
+
+from oracle import slam_oracle as so
+from parity_util import round_frozen
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_max(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def cosine(a, b):
+    a, b = a.float().cpu().flatten(), b.float().cpu().flatten()
+    return torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def build_pair(enc_cfg, llm_cfg, lora_cfg, proj_cfg, seed=42):
+    from slam_llm_b200 import config as C
+    from slam_llm_b200.engine import SlamStepB200
+    om = round_frozen(so.OracleModel.build(enc_cfg, llm_cfg, lora_cfg, proj_cfg, seed=seed))
+    eng = SlamStepB200(C.EncoderCfg(**vars(enc_cfg)), C.LlmCfg(**vars(llm_cfg)),
+                       C.LoraCfg(lora_cfg.r, lora_cfg.alpha, tuple(lora_cfg.targets)) if lora_cfg else None, C.ProjCfg(**vars(proj_cfg)),
+                       device="cuda:0", enc_weights=om.enc_w, llm_weights=om.llm_w, lora_weights=om.lora_w, proj_weights=om.proj_w)
+    return om, eng
+
+
+def to_dev(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+CASES = {
+    # dh = 64 decoder, GQA 2:1, LoRA on q,v (asr_librispeech defaults), left + right padding in the batch
+    "tiny_dh64": dict(enc=so.EncoderCfg(80, 1500, 128, 2, 2), llm=so.LlmCfg(512, 256, 2, 4, 2, 512, 10000.0, 1e-5),
+                      lora=so.LoraCfg(8, 32, ("q_proj", "v_proj")), proj=so.ProjCfg("linear", 5, 128), B=2, n=32000, left=[0, 3]),
+    # dh = 128 decoder (Llama-3 head shape), GQA 4:1, LoRA on all seven linears (aispeech_asr style), 128-mel encoder
+    "dh128_all_lora": dict(enc=so.EncoderCfg(128, 1500, 192, 3, 2), llm=so.LlmCfg(1024, 512, 3, 4, 1, 768, 500000.0, 1e-5),
+                           lora=so.LoraCfg(16, 32, so.LLM_LINEARS), proj=so.ProjCfg("linear", 5, 256), B=3, n=48000, left=[2, 0, 5]),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_step_matches_oracle(name):
+    c = CASES[name]
+    om, eng = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    batch = so.synthetic_batch(c["B"], c["n"], c["llm"].vocab, prompt_len=6, answer_len=9, left_pad=c["left"], seed=7)
+    ref = om.step(dict(batch), lr=1e-3, weight_decay=0.01)
+
+    gb = to_dev(batch)
+    mel = eng.log_mel(gb["audio_pcm"])
+    ref_mel = so.batch_log_mel(batch["audio_pcm"], c["enc"].n_mels)
+    assert (mel.cpu() - ref_mel).abs().max().item() < 2e-3                     # log-mel: absolute, on the (x+4)/4 scale
+
+    enc_out = eng.encoder.forward(mel)
+    assert rel_max(enc_out, ref["encoder_out"]) < 2e-2 and cosine(enc_out, ref["encoder_out"]) > 0.999
+
+    loss, acc, _ = eng.forward(gb, train=True)
+    eng.backward()
+    assert abs(loss.item() - ref["loss"].item()) / ref["loss"].item() < 5e-3, (loss.item(), ref["loss"].item())
+    assert abs(acc.item() - ref["acc"].item()) < 1e-6 or abs(acc.item() - ref["acc"].item()) <= 1.0 / 9 + 1e-6
+
+    grads = eng.trainable_state("grad")
+    assert set(grads) == set(ref["grads"])
+    gmax = max(g.norm().item() for g in ref["grads"].values())
+    checked = 0
+    for k, g_ref in ref["grads"].items():
+        if g_ref.norm().item() < 1e-3 * gmax:
+            continue  # numerically negligible tensors carry no signal in bf16
+        g = grads[k]
+        assert cosine(g, g_ref) > 0.99, (k, cosine(g, g_ref))
+        assert rel_l2(g, g_ref) < 3e-2, (k, rel_l2(g, g_ref))
+        checked += 1
+    assert checked >= 8
+
+    # one AdamW step (lr 1e-3, wd 0.01): parameters must move the same way
+    before = {k: v.clone() for k, v in eng.trainable_state().items()}
+    eng.optimizer_step(1e-3, 0.01)
+    after = eng.trainable_state()
+    new_ref = om.trainable()
+    for k in ("encoder_projector.linear2.weight", "encoder_projector.linear1.bias"):
+        upd, upd_ref = (after[k] - before[k]).cpu(), new_ref[k].detach() - before[k].cpu()
+        assert cosine(upd, upd_ref) > 0.98, (k, cosine(upd, upd_ref))
+
+
+def test_full_logits_eval_path_matches_oracle():
+    c = CASES["tiny_dh64"]
+    om, eng = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    batch = so.synthetic_batch(2, 32000, c["llm"].vocab, prompt_len=6, answer_len=9, left_pad=[0, 3], seed=11, with_mel=True, n_mels=80)
+    out = om.forward(dict(batch), return_all=True)
+    gb = to_dev(batch)
+    loss, acc, logits = eng.forward(gb, train=False, full_logits=True)
+    valid = batch["attention_mask"]
+    ref_logits = out["logits"].detach()
+    sel = valid[:, :, None].expand_as(ref_logits)
+    assert rel_max(logits.cpu()[sel], ref_logits[sel]) < 2e-2
+    assert cosine(logits.cpu()[sel], ref_logits[sel]) > 0.999
+    assert abs(loss.item() - out["loss"].item()) / out["loss"].item() < 5e-3
+
+
+def test_golden_fixture_matches_engine():
+    """The committed golden vectors (generated by tests/golden/make_golden.py from the oracle) vs the CUDA path."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "step_tiny.pt"))
+    cfg = g["cfg"]
+    enc, llm = so.EncoderCfg(*cfg["enc"]), so.LlmCfg(*cfg["llm"])
+    lora, proj = so.LoraCfg(cfg["lora"][0], cfg["lora"][1], tuple(cfg["lora"][2])), so.ProjCfg(*cfg["proj"])
+    om, eng = build_pair(enc, llm, lora, proj, seed=cfg["seed"])
+    batch = so.synthetic_batch(*cfg["batch_args"], **cfg["batch_kwargs"])
+    loss, acc, _ = eng.forward(to_dev(batch), train=True)
+    eng.backward()
+    assert abs(loss.item() - g["loss"]) / g["loss"] < 5e-3
+    grads = eng.trainable_state("grad")
+    for k, (norm, head) in g["grad_probe"].items():
+        gk = grads[k].float().cpu()
+        assert abs(gk.norm().item() - norm) / max(norm, 1e-12) < 3e-2, k
+        if norm > 1e-4:
+            assert cosine(gk.flatten()[: head.numel()], head) > 0.98, k
