@@ -550,8 +550,7 @@ class SlamStepB200:
         else:
             mel = mel.to(dev, F32)
         B, S = ids.shape
-        if train:
-            self.llm.pack_lora()
+        self.llm.pack_lora()                                                               # adapters change every optimizer step
         enc_out = self.encoder.forward(mel)
         aud = self.projector.forward(enc_out, save=train)
         x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)

@@ -42,6 +42,16 @@ def launch_count() -> int:
     return int(_l.load().slam_launch_count())
 
 
+_GEMM_LOG = None
+
+
+def set_gemm_event_log(log) -> None:
+    """bench.py instrumentation: when `log` is a list, every gemm() appends (algorithmic_flops, start_event, end_event)
+    recorded on the launching stream (no synchronisation here)."""
+    global _GEMM_LOG
+    _GEMM_LOG = log
+
+
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
@@ -83,6 +93,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     g.alpha = alpha
     g.m, g.n = M, N
     g.block_n = block_n
+    if _GEMM_LOG is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
+        e1.record()
+        _GEMM_LOG.append((2.0 * M * N * (K1 + g.k2), e0, e1))
+        return out
     _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
     return out
 
