@@ -486,19 +486,31 @@ class SlamStepB200:
 
     def __init__(self, enc_cfg: EncoderCfg, llm_cfg: LlmCfg, lora_cfg: Optional[LoraCfg], proj_cfg: ProjCfg, device="cuda:0",
                  enc_weights=None, llm_weights=None, lora_weights=None, proj_weights=None, seed: int = 42, lora_b_std: float = 0.0):
-        self.device = _require_cuda(device)
-        torch.cuda.set_device(self.device)
-        self.enc_cfg, self.llm_cfg, self.lora_cfg, self.proj_cfg = enc_cfg, llm_cfg, lora_cfg, proj_cfg
-        self.arena = TrainableArena()
-        self.encoder = WhisperEncoderB200(enc_cfg, enc_weights, self.device, seed=seed)
-        self.projector = ProjectorB200(enc_cfg, llm_cfg, proj_cfg, self.arena)
-        self.llm = LlamaLoRAB200(llm_cfg, lora_cfg, self.arena, self.device, llm_weights, seed=seed + 1)
-        self.arena.finalize(self.device)
-        self.projector.init_weights(proj_weights, seed=seed + 3)
-        self.llm.init_lora(lora_weights, seed=seed + 2, b_std=lora_b_std)
-        self.filters_t = mel_filterbank(enc_cfg.n_mels).t().contiguous().to(self.device)
-        self._stats = None
+        device = _require_cuda(device)
+        torch.cuda.set_device(device)
+        arena = TrainableArena()
+        encoder = WhisperEncoderB200(enc_cfg, enc_weights, device, seed=seed)
+        projector = ProjectorB200(enc_cfg, llm_cfg, proj_cfg, arena)
+        llm = LlamaLoRAB200(llm_cfg, lora_cfg, arena, device, llm_weights, seed=seed + 1)
+        arena.finalize(device)
+        projector.init_weights(proj_weights, seed=seed + 3)
+        llm.init_lora(lora_weights, seed=seed + 2, b_std=lora_b_std)
+        self._assemble(encoder, projector, llm, arena, device)
+
+    @classmethod
+    def from_parts(cls, encoder: WhisperEncoderB200, projector: ProjectorB200, llm: LlamaLoRAB200, arena: TrainableArena, device) -> "SlamStepB200":
+        """Assemble a step from already-built components sharing one (finalized) arena (used by the slam_llm mirror)."""
+        self = cls.__new__(cls)
+        self._assemble(encoder, projector, llm, arena, _require_cuda(device))
+        return self
+
+    def _assemble(self, encoder, projector, llm, arena, device) -> None:
+        self.device = device
+        self.enc_cfg, self.llm_cfg, self.lora_cfg, self.proj_cfg = encoder.cfg, llm.cfg, llm.lora, projector.cfg
+        self.arena, self.encoder, self.projector, self.llm = arena, encoder, projector, llm
+        self.filters_t = mel_filterbank(self.enc_cfg.n_mels).t().contiguous().to(device)
         self._ctx = None
+        self.micro_steps = 0   # backward() calls since the last optimizer step (gradient accumulation)
 
     # ------------------------------------------------------------------ state dict in the reference's key names
     def trainable_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
@@ -579,6 +591,7 @@ class SlamStepB200:
         c = self._ctx
         self._ctx = None
         dev = self.device
+        carry = self.arena.grad.clone() if self.micro_steps > 0 else None                 # gradient accumulation: kernels overwrite
         gs = (1.0 / c["nv"]) if grad_out is None else (grad_out.to(dev, F32).reshape(1) / c["nv"])
         gs = gs.contiguous()
         logits = c["logits"]
@@ -596,9 +609,13 @@ class SlamStepB200:
         dx = self.llm.backward(dxf)
         daud = ops.embed_merge_bwd(c["mod_mask"], dx.contiguous(), c["Ta"])
         self.projector.backward(daud)
+        if carry is not None:
+            self.arena.grad.add_(carry)
+        self.micro_steps += 1
 
     def optimizer_step(self, lr: float, weight_decay: float = 0.0, grad_div: float = 1.0) -> None:
         self.arena.adamw_step(lr, weight_decay, grad_div=grad_div)
+        self.micro_steps = 0
 
     def train_step(self, batch, lr: float = 1e-4, weight_decay: float = 0.0, world_size: int = 1):
         loss, acc, _ = self.forward(batch, train=True)

@@ -1,0 +1,338 @@
+"""Model assembly — the drop-in boundary of the hot path (reference: src/slam_llm/models/slam_model.py:21-456).
+
+Same factories and the same `slam_model(encoder, llm, encoder_projector, tokenizer, train_config, model_config, **kw)`
+class as the reference, so recipes (examples/asr_librispeech/model/slam_model_asr.py) import and subclass it unchanged;
+`forward(**batch) -> (outputs, acc)` runs the whole step on slam_llm_b200 kernels:
+
+  audio_pcm -> log-mel (GPU) | audio_mel -> Whisper encoder -> projector -> fused embedding gather+merge
+  -> Llama decoder (frozen bf16 base + fused LoRA tiles) -> lm_head on labelled rows -> fused CE/argmax
+  `outputs.loss.backward()` -> dgrad through frozen weights, grads for projector + LoRA into one flat fp32 arena.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import types
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from slam_llm.utils.config_utils import generate_peft_config
+from slam_llm.utils.metric import compute_accuracy  # noqa: F401  (re-exported for recipes)
+from slam_llm.utils.train_utils import print_model_size, print_module_size
+from slam_llm_b200.config import ATTN_LINEARS, LlmCfg, ProjCfg
+from slam_llm_b200.engine import LlamaLoRAB200, ProjectorB200, SlamStepB200, TrainableArena
+
+logger = logging.getLogger(__name__)
+
+
+def _rank(train_config) -> int:
+    return int(os.environ["RANK"]) if train_config.enable_fsdp or train_config.enable_ddp else 0
+
+
+def model_factory(train_config, model_config, **kwargs):
+    """slam_model.py:21-51."""
+    tokenizer = setup_tokenizer(train_config, model_config, **kwargs)
+    encoder = setup_encoder(train_config, model_config, **kwargs)
+    llm = setup_llm(train_config, model_config, **kwargs)
+    encoder_projector = setup_encoder_projector(train_config, model_config, **kwargs)
+    model = slam_model(encoder, llm, encoder_projector, tokenizer, train_config, model_config, **kwargs)
+    ckpt_path = kwargs.get("ckpt_path", None)
+    if ckpt_path is not None:
+        logger.info("loading other parts from: {}".format(ckpt_path))
+        ckpt_dict = torch.load(ckpt_path, map_location="cpu")
+        model.load_state_dict(ckpt_dict, strict=False)
+    print_model_size(model, train_config, _rank(train_config))
+    return model, tokenizer
+
+
+def setup_tokenizer(train_config, model_config, **kwargs):
+    """slam_model.py:54-65."""
+    from transformers import AutoTokenizer
+    tokenizer = AutoTokenizer.from_pretrained(model_config.llm_path)
+    tokenizer.pad_token_id = tokenizer.eos_token_id
+    return tokenizer
+
+
+def setup_encoder(train_config, model_config, **kwargs):
+    """slam_model.py:68-116 (Whisper path; alternate encoders are out of scope of the B200 hot path)."""
+    encoder_list = model_config.encoder_name.split(",") if model_config.encoder_name else []
+    if len(encoder_list) == 0:
+        return None
+    encoder_name = encoder_list[0]
+    if len(encoder_list) != 1 or encoder_name not in ("whisper", "qwen-audio"):
+        raise NotImplementedError(f"encoder_name={model_config.encoder_name!r}: only the Whisper encoder is on the B200 path (SURVEY.md §2.1)")
+    from slam_llm.models.encoder import WhisperWrappedEncoder
+    encoder = WhisperWrappedEncoder.load(model_config)
+    print_module_size(encoder, encoder_name, _rank(train_config))
+    if train_config.freeze_encoder:
+        for _, param in encoder.named_parameters():
+            param.requires_grad = False
+        encoder.eval()
+    else:
+        raise NotImplementedError("freeze_encoder=false: the B200 path trains projector + LoRA only (encoder frozen, as every asr_* recipe sets)")
+    return encoder
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LLM module: HF LlamaForCausalLM + peft LoRA surface over LlamaLoRAB200
+# ---------------------------------------------------------------------------------------------------------------------
+def _load_llm_cfg(llm_path: str) -> LlmCfg:
+    with open(os.path.join(llm_path, "config.json")) as f:
+        c = json.load(f)
+    if c.get("model_type", "llama") not in ("llama", "mistral"):
+        raise NotImplementedError(f"model_type={c.get('model_type')!r}: the B200 decoder implements the Llama architecture")
+    return LlmCfg(vocab=c["vocab_size"], d=c["hidden_size"], layers=c["num_hidden_layers"], heads=c["num_attention_heads"],
+                  kv_heads=c.get("num_key_value_heads", c["num_attention_heads"]), ffn=c["intermediate_size"],
+                  rope_theta=float(c.get("rope_theta", 10000.0)), eps=float(c.get("rms_norm_eps", 1e-5)))
+
+
+def _load_llm_weights(llm_path: str) -> Optional[Dict[str, torch.Tensor]]:
+    files = sorted(f for f in os.listdir(llm_path) if f.endswith(".safetensors"))
+    if not files:
+        return None
+    from safetensors.torch import load_file
+    out: Dict[str, torch.Tensor] = {}
+    for f in files:
+        out.update(load_file(os.path.join(llm_path, f)))
+    if "lm_head.weight" not in out:
+        out["lm_head.weight"] = out["model.embed_tokens.weight"]
+    return out
+
+
+class _Embedding(nn.Module):
+    """`llm.model.embed_tokens` (probed at slam_model.py:375-380).  The step itself uses the fused gather+merge kernel."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = [owner]
+
+    @property
+    def weight(self):
+        return self._owner[0].b200.embed
+
+    def forward(self, input_ids):
+        return torch.nn.functional.embedding(input_ids.to(self.weight.device), self.weight)
+
+
+def _set_param(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], param)
+
+
+class LlamaB200ForCausalLM(nn.Module):
+    """Frozen Llama decoder (+ optional LoRA adapters under peft-0.6 key names).  Weights are materialised when the
+    module is bound to a step arena by slam_model.__init__."""
+
+    def __init__(self, cfg: LlmCfg, llm_path: str, lora_cfg, use_peft: bool):
+        super().__init__()
+        self.cfg, self.llm_path, self.lora_cfg, self.use_peft = cfg, llm_path, lora_cfg if use_peft else None, use_peft
+        self.b200: Optional[LlamaLoRAB200] = None
+        self._step = None
+        D, Dkv, F, V, L = cfg.d, cfg.dkv, cfg.ffn, cfg.vocab, cfg.layers
+        self.num_frozen_params = 2 * V * D + L * (2 * D * D + 2 * D * Dkv + 3 * D * F + 2 * D) + D
+
+    # PeftModel.__getattr__ forwards unknown attributes to base_model; `llm.model` must reach the causal-LM wrapper
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name == "model":
+                mods = self.__dict__.get("_modules", {})
+                if "base_model" in mods:
+                    return mods["base_model"]._modules["model"]
+            raise
+
+    def bind(self, arena: TrainableArena, device) -> None:
+        weights = _load_llm_weights(self.llm_path)
+        if weights is None:
+            logger.warning(f"no *.safetensors under {self.llm_path}: RANDOM-INIT {self.cfg} (offline / benchmark mode)")
+        self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights)
+
+    def register_views(self, arena: TrainableArena) -> None:
+        """Expose the embedding module and the LoRA adapters under the reference / peft key names."""
+        causal = nn.Module()          # LlamaForCausalLM
+        inner = nn.Module()           # LlamaModel
+        inner.add_module("embed_tokens", _Embedding(self))
+        causal.add_module("model", inner)
+        if self.use_peft:
+            lora_model = nn.Module()  # peft LoraModel
+            lora_model.add_module("model", causal)
+            self.add_module("base_model", lora_model)
+            for key, view in self.b200.lora_state().items():
+                _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
+        else:
+            self.add_module("model", causal)
+
+    def print_trainable_parameters(self):
+        trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        total = trainable + self.num_frozen_params
+        logger.info(f"trainable params: {trainable:,d} || all params: {total:,d} || trainable%: {100 * trainable / total:.4f}")
+
+    def forward(self, inputs_embeds=None, attention_mask=None, labels=None, **kw):
+        if self._step is None:
+            raise RuntimeError("LLM is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
+        return self._step.llm_forward(inputs_embeds, attention_mask, labels)
+
+    def generate(self, *a, **kw):
+        raise NotImplementedError("generate() (beam-search decode path) is outside the training-step hot path (SURVEY.md §8f rank 4)")
+
+
+def setup_llm(train_config, model_config, **kwargs):
+    """slam_model.py:118-221: frozen base LLM + LoRA adapters from train_config.peft_config."""
+    if train_config.quantization:
+        raise NotImplementedError("8-bit quantised loading is out of scope of the B200 path")
+    if not train_config.freeze_llm:
+        raise NotImplementedError("freeze_llm=false (full fine-tune) needs wgrad for every linear: SURVEY.md §8f rank 3, not built yet")
+    if kwargs.get("peft_ckpt", None):
+        raise NotImplementedError("peft_ckpt directories: pass the trainable-only model.pt via ckpt_path instead")
+    cfg = _load_llm_cfg(model_config.llm_path)
+    lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
+    if lora_cfg is not None and lora_cfg.dropout > 0:
+        logger.warning(f"lora_dropout={lora_cfg.dropout} is treated as 0 on the B200 path (dropout on the LoRA branch is not implemented yet)")
+    model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, bool(train_config.use_peft))
+    print_module_size(model, model_config.llm_name, _rank(train_config))
+    model.eval()
+    if train_config.use_peft:
+        logger.info("setup peft...")
+    return model
+
+
+def setup_encoder_projector(train_config, model_config, **kwargs):
+    """slam_model.py:223-236."""
+    if model_config.encoder_projector == "linear":
+        from slam_llm.models.projector import EncoderProjectorConcat
+        encoder_projector = EncoderProjectorConcat(model_config)
+    elif model_config.encoder_projector == "cov1d-linear":
+        from slam_llm.models.projector import EncoderProjectorCov1d
+        encoder_projector = EncoderProjectorCov1d(model_config)
+    elif model_config.encoder_projector == "q-former":
+        from slam_llm.models.projector import EncoderProjectorQFormer
+        encoder_projector = EncoderProjectorQFormer(model_config)
+    else:
+        return None
+    print_module_size(encoder_projector, model_config.encoder_projector, _rank(train_config))
+    return encoder_projector
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class _StepLoss(torch.autograd.Function):
+    """Connects the device-computed loss to autograd: `loss.backward()` (utils/train_utils.py:130,152) runs the B200
+    backward, which writes the projector/LoRA gradients straight into the flat arena (p.grad are views of it)."""
+
+    @staticmethod
+    def forward(ctx, anchor, loss, owner):
+        ctx.owner = owner
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.owner._backward(grad_out)
+        return None, None, None
+
+
+class _Outputs(types.SimpleNamespace):
+    pass
+
+
+class slam_model(nn.Module):
+    def __init__(self, encoder: nn.Module, llm: nn.Module, encoder_projector: nn.Module, tokenizer, train_config, model_config, **kwargs):
+        super().__init__()
+        self.encoder = encoder
+        self.llm = llm
+        self.encoder_projector = encoder_projector
+        self.tokenizer = tokenizer
+        self.metric = kwargs.get("metric", "acc")
+        self.train_config = train_config
+        self.model_config = model_config
+        self.dataset_config = kwargs.get("dataset_config", None)   # reference quirk Q4
+        if not torch.cuda.is_available():
+            raise RuntimeError("slam_model needs a CUDA (B200) device: the hot path has no CPU fallback")
+        if encoder is None or encoder_projector is None or not isinstance(llm, LlamaB200ForCausalLM):
+            raise NotImplementedError("the B200 step needs a Whisper encoder, a linear projector and a Llama-architecture LLM")
+        device = torch.device("cuda", torch.cuda.current_device())
+        arena = TrainableArena()
+        proj_cfg = ProjCfg("linear", encoder_projector.k, encoder_projector.linear1.out_features)
+        eng_proj = ProjectorB200(encoder.b200.cfg, llm.cfg, proj_cfg, arena)
+        llm.bind(arena, device)
+        arena.finalize(device)
+        encoder_projector.bind(eng_proj, arena)
+        llm.b200.init_lora(None)                                    # peft init: A kaiming-uniform, B zeros
+        llm.register_views(arena)
+        self.b200 = SlamStepB200.from_parts(encoder.b200, eng_proj, llm.b200, arena, device)
+        llm._step = self
+        arena.param.requires_grad_(True)
+        self._grad_views_set = False
+        self.ddp_world_size = 1
+        self.ddp_sync = True
+
+    # nn.Module.to()/cuda() would re-materialise the arena views as independent tensors: the step is already on the GPU
+    def _apply(self, fn, recurse=True):
+        return self
+
+    # ---- gradient plumbing
+    def _bind_grad_views(self):
+        grads = self.b200.trainable_state("grad")
+        for name, p in self.named_parameters():
+            if p.requires_grad and name in grads:
+                p.grad = grads[name]
+
+    def _backward(self, grad_out):
+        self.b200.backward(grad_out)
+        if self.ddp_world_size > 1 and self.ddp_sync:
+            torch.distributed.all_reduce(self.b200.arena.grad)     # DDP: the one data-path collective (finetune.py:181-184)
+        self._bind_grad_views()
+
+    # ---- decoder entry used by recipes that override forward() and call self.llm(...) themselves
+    def llm_forward(self, inputs_embeds, attention_mask, labels):
+        raise NotImplementedError("calling self.llm(inputs_embeds=...) directly is not wired yet; use slam_model.forward")
+
+    # ---- forward (slam_model.py:283-407)
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None, **kwargs):
+        audio_mel = kwargs.get("audio_mel", None)
+        audio_pcm = kwargs.get("audio_pcm", None)
+        modality_mask = kwargs.get("modality_mask", None)
+        if audio_mel is None and audio_pcm is None:
+            raise NotImplementedError("the B200 step needs audio_mel or audio_pcm in the batch (Whisper recipes)")
+        if self.train_config.freeze_encoder:
+            self.encoder.eval()
+        batch = dict(input_ids=input_ids, labels=labels, attention_mask=attention_mask, modality_mask=modality_mask)
+        if audio_mel is not None:
+            batch["audio_mel"] = audio_mel
+        else:
+            batch["audio_pcm"] = audio_pcm
+        for k in ("_rows", "_targets"):
+            if kwargs.get(k, None) is not None:
+                batch[k] = kwargs[k]
+        if kwargs.get("inference_mode", False):
+            return self._inputs_embeds(batch), attention_mask
+        train = torch.is_grad_enabled() and labels is not None
+        full = (not train) or bool(self.train_config.get("b200_full_logits", False))
+        loss, acc, logits = self.b200.forward(batch, train=train, full_logits=full)
+        if train:
+            loss = _StepLoss.apply(self.b200.arena.param, loss, self)
+        outputs = _Outputs(loss=loss, logits=logits)
+        if not self.metric:
+            acc = -1
+        return outputs, acc
+
+    def _inputs_embeds(self, batch):
+        from slam_llm_b200 import ops
+        dev = self.b200.device
+        mel = batch.get("audio_mel")
+        mel = self.b200.log_mel(batch["audio_pcm"].to(dev, torch.float32)) if mel is None else mel.to(dev, torch.float32)
+        aud = self.b200.projector.forward(self.b200.encoder.forward(mel), save=False)
+        return ops.embed_merge(batch["input_ids"].to(dev).contiguous(), batch["modality_mask"].to(dev).to(torch.uint8).contiguous(), aud,
+                               self.b200.llm.embed)
+
+    @torch.no_grad()
+    def generate(self, *a, **kw):
+        raise NotImplementedError("generate() (decode path) is outside the training-step hot path (SURVEY.md §8f rank 4)")
