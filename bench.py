@@ -109,12 +109,35 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (port of the reference's eager path) on the host cores, bounded sample
 # ----------------------------------------------------------------------------------------------------------------------
+def pick_cpu_threads():
+    """Use as many host threads as actually help: the box may expose more logical CPUs than its cgroup quota grants, in
+    which case torch with os.cpu_count() threads is several times SLOWER.  Time one decoder-MLP-shaped matmul at a few
+    thread counts and keep the fastest (the count is reported as cpu_baseline.cores)."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (avail, avail // 2, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    a, b = torch.randn(401, 4096), torch.randn(4096, 14336)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.mm(a, b)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.mm(a, b)
+        t = time.perf_counter() - t0
+        if t < best_t * 0.95:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference(wl, steps, warmup, budget_s=150.0, quiet=True):
     """Times the CPU restatement of the reference path (oracle/slam_oracle.py) on one utterance with a reduced number of
     encoder/decoder layers and extrapolates linearly in the layer counts to the full depth.  Returns audio-s/s."""
     from oracle import slam_oracle as so
-    torch.set_num_threads(os.cpu_count() or 1)
-    cores = torch.get_num_threads()
+    cores = pick_cpu_threads()
     enc_full, llm_full = so.WHISPER[wl["enc"]], so.LLM[wl["llm"]]
     lora, proj = so.LoraCfg(wl["r"], wl["alpha"], tuple(wl["targets"])), so.ProjCfg("linear", 5, 2048)
     wl1 = dict(wl, batch=1)

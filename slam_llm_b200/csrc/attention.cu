@@ -52,55 +52,92 @@ struct AttnP {
   float* dq_accum;
 };
 
-// rows x DH bf16 tile, global (row stride ld) -> shared (row pitch DH+8); rows >= valid are zero-filled
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// rows x DH bf16 tile, global (row stride ld) -> shared (row pitch DH+8) with cp.async (no register staging, the
+// copies of the NEXT tile overlap the MMAs of the current one); rows >= valid are zero-filled (src-size 0)
 template <int DH, int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long ld, int valid) {
   constexpr int PITCH = DH + 8;
   constexpr int VPR = DH / 8;
+#pragma unroll
   for (int i = threadIdx.x; i < ROWS * VPR; i += THREADS) {
     const int r = i / VPR, c = (i - r * VPR) * 8;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (r < valid) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * ld + c);
-    *reinterpret_cast<uint4*>(dst + r * PITCH + c) = val;
+    const bool ok = r < valid;
+    cp_async16(dst + r * PITCH + c, src + (ok ? static_cast<long long>(r) * ld + c : 0), ok ? 16 : 0);
   }
 }
 
 // ------------------------------------------------------------------------------------------- forward
 template <int DH>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
+__global__ void __launch_bounds__(128, DH == 64 ? 4 : 2) attn_fwd_kernel(const AttnP p) {
   constexpr int BM = 64, BN = 64, PITCH = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
-  bf16* sK = sQ + BM * PITCH;
-  bf16* sV = sK + BN * PITCH;
+  bf16* sKb = sQ + BM * PITCH;                 // 2 stages of K
+  bf16* sVb = sKb + 2 * BN * PITCH;            // 2 stages of V
+  uint8_t* sMask = reinterpret_cast<uint8_t*>(sVb + 2 * BN * PITCH);  // 2 x 64 key-mask bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.hq / p.hkv);
   const int q0 = blockIdx.x * BM;
+  const int n_end = p.causal ? min(p.sk, q0 + BM) : p.sk;
+  const int n_tiles = (n_end + BN - 1) / BN;
+  const bf16* kbase = p.k + static_cast<long long>(b) * p.sk * p.ldk + hk * DH;
+  const bf16* vbase = p.v + static_cast<long long>(b) * p.sk * p.ldv + hk * DH;
+  const uint8_t* mk = p.key_mask != nullptr ? p.key_mask + static_cast<long long>(b) * p.sk : nullptr;
 
+  auto prefetch = [&](int t) {
+    const int n0 = t * BN;
+    load_tile<DH, BN, 128>(sKb + (t & 1) * BN * PITCH, kbase + static_cast<long long>(n0) * p.ldk, p.ldk, min(BN, p.sk - n0));
+    load_tile<DH, BN, 128>(sVb + (t & 1) * BN * PITCH, vbase + static_cast<long long>(n0) * p.ldv, p.ldv, min(BN, p.sk - n0));
+    cp_async_commit();
+  };
   load_tile<DH, BM, 128>(sQ, p.q + (static_cast<long long>(b) * p.sq + q0) * p.ldq + h * DH, p.ldq, min(BM, p.sq - q0));
-  __syncthreads();
-  uint32_t qf[DH / 16][4];
-#pragma unroll
-  for (int ks = 0; ks < DH / 16; ++ks)
-    ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ks * 16 + (lane >> 4) * 8);
+  prefetch(0);
+  uint8_t mreg = 1;
+  if (mk != nullptr && threadIdx.x < BN) {
+    const int col = threadIdx.x;
+    sMask[col] = col < p.sk ? mk[col] : 0;
+  }
 
+  uint32_t qf[DH / 16][4];
   float o[DH / 8][4];
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
   float mrow[2] = {-CUDART_INF_F, -CUDART_INF_F};
   float lrow[2] = {0.0f, 0.0f};
   const float scale_log2 = p.scale * kLog2e;
-  const int n_end = p.causal ? min(p.sk, q0 + BM) : p.sk;
-  const bf16* kbase = p.k + static_cast<long long>(b) * p.sk * p.ldk + hk * DH;
-  const bf16* vbase = p.v + static_cast<long long>(b) * p.sk * p.ldv + hk * DH;
-  const uint8_t* mk = p.key_mask != nullptr ? p.key_mask + static_cast<long long>(b) * p.sk : nullptr;
 
-  for (int n0 = 0; n0 < n_end; n0 += BN) {
-    __syncthreads();
-    load_tile<DH, BN, 128>(sK, kbase + static_cast<long long>(n0) * p.ldk, p.ldk, min(BN, p.sk - n0));
-    load_tile<DH, BN, 128>(sV, vbase + static_cast<long long>(n0) * p.ldv, p.ldv, min(BN, p.sk - n0));
-    __syncthreads();
+  for (int t = 0; t < n_tiles; ++t) {
+    const int n0 = t * BN;
+    cp_async_wait<0>();
+    __syncthreads();                       // tile t (and Q on t == 0) landed; everyone is done with tile t-1
+    if (t + 1 < n_tiles) {
+      prefetch(t + 1);                     // overlaps the MMAs below
+      if (mk != nullptr && threadIdx.x < BN) {
+        const int col = n0 + BN + threadIdx.x;
+        mreg = col < p.sk ? mk[col] : 0;
+      }
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ks * 16 + (lane >> 4) * 8);
+    }
+    const bf16* sK = sKb + (t & 1) * BN * PITCH;
+    const bf16* sV = sVb + (t & 1) * BN * PITCH;
+    const uint8_t* sM = sMask + (t & 1) * BN;
 
     float s[BN / 8][4];
 #pragma unroll
@@ -115,16 +152,22 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
         mma16816(s[2 * nb2 + 1], qf[ks], kb[2], kb[3]);
       }
     }
-    // scale + mask (log2 domain)
+    // scale + mask (log2 domain); only boundary / diagonal / masked tiles need the per-element test
+    const bool need_mask = (n0 + BN > p.sk) || (p.causal && n0 + BN > q0) || mk != nullptr;
 #pragma unroll
     for (int nb = 0; nb < BN / 8; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = n0 + nb * 8 + 2 * (lane & 3) + (e & 1);
-        const int row = q0 + warp * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
-        bool ok = col < p.sk && (!p.causal || col <= row);
-        if (ok && mk != nullptr) ok = mk[col] != 0;
-        s[nb][e] = ok ? s[nb][e] * scale_log2 : -CUDART_INF_F;
+        float v = s[nb][e] * scale_log2;
+        if (need_mask) {
+          const int cl = nb * 8 + 2 * (lane & 3) + (e & 1);
+          const int col = n0 + cl;
+          const int row = q0 + warp * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+          bool ok = col < p.sk && (!p.causal || col <= row);
+          if (ok && mk != nullptr) ok = sM[cl] != 0;
+          v = ok ? v : -CUDART_INF_F;
+        }
+        s[nb][e] = v;
       }
     }
     // online softmax, two rows per thread
@@ -171,6 +214,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
         mma16816(o[2 * nb2 + 1], a, vb[2], vb[3]);
       }
     }
+    if (t + 1 < n_tiles && mk != nullptr && threadIdx.x < BN) sMask[((t + 1) & 1) * BN + threadIdx.x] = mreg;
   }
 
   // finalize
@@ -228,11 +272,11 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sK = reinterpret_cast<bf16*>(smem_attn);
   bf16* sV = sK + BN * PITCH;
-  bf16* sQ = sV + BN * PITCH;
-  bf16* sdO = sQ + BQ * PITCH;
-  bf16* sdS = sdO + BQ * PITCH;  // [key][q]
-  float* sLse = reinterpret_cast<float*>(sdS + BN * SPITCH);
-  float* sDelta = sLse + BQ;
+  bf16* sQb = sV + BN * PITCH;             // 2 stages of Q
+  bf16* sdOb = sQb + 2 * BQ * PITCH;       // 2 stages of dO
+  bf16* sdS = sdOb + 2 * BQ * PITCH;       // [key][q]
+  float* sLseB = reinterpret_cast<float*>(sdS + BN * SPITCH);  // 2 stages of lse (log2 domain) ...
+  float* sDeltaB = sLseB + 2 * BQ;                             // ... and delta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hk = blockIdx.y, b = blockIdx.z;
   const int k0 = blockIdx.x * BN;
@@ -257,19 +301,38 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
   }
 
   const int q_start = p.causal ? (k0 / BQ) * BQ : 0;
-  for (int g = 0; g < group; ++g) {
-    const int h = hk * group + g;
-    for (int q0 = q_start; q0 < p.sq; q0 += BQ) {
-      __syncthreads();
-      const int vq = min(BQ, p.sq - q0);
-      load_tile<DH, BQ, 128>(sQ, p.q + (static_cast<long long>(b) * p.sq + q0) * p.ldq + h * DH, p.ldq, vq);
-      load_tile<DH, BQ, 128>(sdO, p.dout + (static_cast<long long>(b) * p.sq + q0) * p.lddo + h * DH, p.lddo, vq);
-      for (int i = threadIdx.x; i < BQ; i += 128) {
-        const long long off = (static_cast<long long>(b) * p.hq + h) * p.sq + q0 + i;
-        sLse[i] = i < vq ? p.lse[off] * kLog2e : 0.0f;
-        sDelta[i] = i < vq ? p.delta[off] : 0.0f;
-      }
-      __syncthreads();
+  const int nq = (p.sq - q_start + BQ - 1) / BQ;
+  const int n_iter = group * nq;
+
+  // stage j of the (head-in-group, query-block) sequence -> shared stage j & 1 (cp.async: overlaps the MMAs of stage j-1)
+  auto prefetch = [&](int j) {
+    const int h = hk * group + j / nq;
+    const int q0 = q_start + (j % nq) * BQ;
+    const int vq = min(BQ, p.sq - q0);
+    const int st = j & 1;
+    load_tile<DH, BQ, 128>(sQb + st * BQ * PITCH, p.q + (static_cast<long long>(b) * p.sq + q0) * p.ldq + h * DH, p.ldq, vq);
+    load_tile<DH, BQ, 128>(sdOb + st * BQ * PITCH, p.dout + (static_cast<long long>(b) * p.sq + q0) * p.lddo + h * DH, p.lddo, vq);
+    if (threadIdx.x < 2 * BQ) {
+      const int i = threadIdx.x % BQ;
+      const bool is_delta = threadIdx.x >= BQ;
+      const long long off = (static_cast<long long>(b) * p.hq + h) * p.sq + q0 + (i < vq ? i : 0);
+      cp_async4((is_delta ? sDeltaB : sLseB) + st * BQ + i, (is_delta ? p.delta : p.lse) + off, i < vq ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+  if (n_iter > 0) prefetch(0);
+
+  for (int j = 0; j < n_iter; ++j) {
+    {
+      const int h = hk * group + j / nq;
+      const int q0 = q_start + (j % nq) * BQ;
+      cp_async_wait<0>();
+      __syncthreads();                      // stage j landed; everyone is done with stage j-1 (and with sdS)
+      if (j + 1 < n_iter) prefetch(j + 1);
+      const bf16* sQ = sQb + (j & 1) * BQ * PITCH;
+      const bf16* sdO = sdOb + (j & 1) * BQ * PITCH;
+      const float* sLse = sLseB + (j & 1) * BQ;
+      const float* sDelta = sDeltaB + (j & 1) * BQ;
 
       // S^T = K_w Q^T and dP^T = V_w dO^T   (16 keys x BQ queries per warp)
       float st[BQ / 8][4], dpt[BQ / 8][4];
@@ -308,7 +371,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
           const int ql = nb * 8 + 2 * (lane & 3) + (e & 1);
           const int qi = q0 + ql;
           const bool ok = key_ok[r] && qi < p.sq && (!p.causal || key <= qi);
-          const float pv = ok ? exp2f(st[nb][e] * scale_log2 - sLse[ql]) : 0.0f;
+          const float pv = ok ? exp2f(st[nb][e] * scale_log2 - sLse[ql] * kLog2e) : 0.0f;
           const float ds = pv * (dpt[nb][e] - sDelta[ql]) * p.scale;
           st[nb][e] = pv;
           dpt[nb][e] = ds;
@@ -445,7 +508,7 @@ static int fill_params(const slam_attn_args* a, AttnP& p, bool bwd) {
 
 template <int DH>
 static int launch_fwd(const AttnP& p, cudaStream_t st) {
-  constexpr int SMEM = 3 * 64 * (DH + 8) * 2;
+  constexpr int SMEM = 5 * 64 * (DH + 8) * 2 + 128;
   static bool set = false;
   if (!set) {
     cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -458,7 +521,7 @@ static int launch_fwd(const AttnP& p, cudaStream_t st) {
 }
 template <int DH, int BQ>
 static int launch_bwd(const AttnP& p, cudaStream_t st) {
-  constexpr int SMEM = (2 * 64 + 2 * BQ) * (DH + 8) * 2 + 64 * (BQ + 8) * 2 + 2 * BQ * 4;
+  constexpr int SMEM = (2 * 64 + 4 * BQ) * (DH + 8) * 2 + 64 * (BQ + 8) * 2 + 4 * BQ * 4;
   static bool set = false;
   if (!set) {
     cudaFuncSetAttribute(attn_bwd_kernel<DH, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

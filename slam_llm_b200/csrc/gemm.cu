@@ -42,10 +42,10 @@ struct GemmKParams {
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BK * 2;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
 };
@@ -329,14 +329,25 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
 
 static int pick_block_n(int m, int n) {
   if (n <= 64) return 64;
-  if (n < 256) return 128;
-  // measured on B200 (profiles/r01_gemm_bench_v0.json): BLOCK_N=128 tiles are shared-memory-bandwidth bound
-  // (~0.65x the per-flop rate of 256), so 256 wins even when it costs an extra partial wave.
+  if (n < 192) return 128;
+  // cost = waves x tile width x per-flop penalty.  Measured on B200 (profiles/r01_gemm_bench_v0.json): BLOCK_N=128 tiles are
+  // shared-memory-bandwidth bound (~0.65x the per-flop rate of 256); 192 re-reads A slightly more often than 256 but fixes
+  // the wave quantisation of the N=4096 / 6144 decoder GEMMs at M=1600 (286 tiles = 1.93 waves instead of 208 = 1.41).
   const int sms = num_sms();
   const int64_t mt = ceil_div(m, GEMM_BM);
-  const double c256 = static_cast<double>(ceil_div(mt * ceil_div(n, 256), sms)) * 256.0;
-  const double c128 = static_cast<double>(ceil_div(mt * ceil_div(n, 128), sms)) * 128.0 * 1.5;
-  return c128 < c256 ? 128 : 256;
+  const int cands[3] = {256, 192, 128};
+  const double pen[3] = {1.0, 1.04, 1.5};
+  double best = 1e30;
+  int best_bn = 256;
+  for (int i = 0; i < 3; ++i) {
+    if (cands[i] > n && i < 2) continue;
+    const double c = static_cast<double>(ceil_div(mt * ceil_div(n, cands[i]), sms)) * cands[i] * pen[i];
+    if (c < best) {
+      best = c;
+      best_bn = cands[i];
+    }
+  }
+  return best_bn;
 }
 
 }  // namespace slam
@@ -357,6 +368,7 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   if (bn == 0) bn = pick_block_n(g->m, g->n);
   switch (bn) {
     case 256: return launch_gemm<256>(g, st);
+    case 192: return launch_gemm<192>(g, st);
     case 128: return launch_gemm<128>(g, st);
     case 64: return launch_gemm<64>(g, st);
     default: set_error("gemm: unsupported block_n %d", bn); return -1;

@@ -216,12 +216,14 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
   zero2d_kernel<<<static_cast<unsigned>(zb), 256, 0, st>>>(c, ldc, p, q);
   SLAM_LAUNCH_CHECK("slam_wgrad_thin.zero");
   const int qblocks = static_cast<int>(ceil_div(q, 64));
-  int ysplit = static_cast<int>(ceil_div(2 * num_sms(), qblocks));
-  if (ysplit < 1) ysplit = 1;
-  const int max_split = static_cast<int>(ceil_div(m, 64));
-  if (ysplit > max_split) ysplit = max_split;
-  const int m_chunk = static_cast<int>(ceil_div(ceil_div(m, ysplit), 32) * 32);
-  ysplit = static_cast<int>(ceil_div(m, m_chunk));
+  // ~128 rows of M per block: many short blocks (atomics merge the partial sums) instead of few long latency-bound ones
+  int m_chunk = 128;
+  int ysplit = static_cast<int>(ceil_div(m, m_chunk));
+  if (static_cast<long long>(ysplit) * qblocks > 16LL * num_sms()) {
+    ysplit = static_cast<int>(ceil_div(16LL * num_sms(), qblocks));
+    m_chunk = static_cast<int>(ceil_div(ceil_div(m, ysplit), 32) * 32);
+    ysplit = static_cast<int>(ceil_div(m, m_chunk));
+  }
   dim3 grid(qblocks, ysplit);
   const bf16* ap = reinterpret_cast<const bf16*>(a);
   const bf16* bp = reinterpret_cast<const bf16*>(b);
