@@ -54,7 +54,8 @@ typedef struct slam_gemm_args {
   const void* residual; int64_t ldr; /* bf16 [M,N] or NULL; added after activation */
   float alpha;
   int32_t m, n;
-  int32_t block_n;                /* 0 = auto; else 64/128/256 */
+  int32_t block_n;                /* tile override: 0 = auto; 64/128/192/256 = BLOCK_N with 128-row tiles;
+                                     BLOCK_M*1000+BLOCK_N (e.g. 256256) = explicit 256-row tile */
 } slam_gemm_args;
 int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
 

@@ -8,7 +8,9 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) with both operands
 //               read from shared memory through UMMA descriptors, fp32 accumulator in TMEM;
 //               tcgen05.commit releases ring slots / publishes the accumulator;
-//   warp 2      TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1);
+//   warp 2      TMEM allocator (BLOCK_M=128: 2 accumulator stages so the epilogue of tile i overlaps tile i+1;
+//               BLOCK_M=256: two M=128 accumulators that SHARE every B tile — the mainloop is bound by the bytes one SM can
+//               keep in flight from L2 (~60 B/clk/SM measured), so 256x256 tiles need 1/3 less traffic per MMA cycle);
 //   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> alpha/bias/activation/residual ->
 //               16-byte global stores (bf16 or f32).
 // The K loop runs over TWO operand pairs back to back ("dual K segment"): the base weights and the
@@ -22,7 +24,6 @@
 
 namespace slam {
 
-constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 
@@ -40,23 +41,31 @@ struct GemmKParams {
   float alpha;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_M, int BLOCK_N>
 struct GemmCfg {
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int HALVES = BLOCK_M / 128;             // M=128 accumulators per tile
+  static constexpr int ACC_STAGES = BLOCK_M == 128 ? 2 : 1;
+  static constexpr int A_BYTES = BLOCK_M * GEMM_BK * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BK * 2;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);  // power of two
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
+  static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_M, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_M, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+  constexpr int HALVES = Cfg::HALVES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -117,11 +126,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           void* dA = sA + stage * Cfg::A_BYTES;
           void* dB = sB + stage * Cfg::B_BYTES;
           if (kb < p.kb1) {
-            tma_load_2d(dA, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * GEMM_BM);
+            tma_load_2d(dA, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * BLOCK_M);
             tma_load_2d(dB, &tmB, &full_bar[stage], kb * GEMM_BK, n_tile * BLOCK_N);
           } else {
             const int k2 = kb - p.kb1;
-            tma_load_2d(dA, &tmA2, &full_bar[stage], k2 * GEMM_BK, m_tile * GEMM_BM);
+            tma_load_2d(dA, &tmA2, &full_bar[stage], k2 * GEMM_BK, m_tile * BLOCK_M);
             tma_load_2d(dB, &tmB2, &full_bar[stage], k2 * GEMM_BK, n_tile * BLOCK_N);
           }
         }
@@ -130,15 +139,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N);
     uint32_t kc = 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u;
-      const uint32_t aph = (it >> 1) & 1u;
+      const uint32_t acc = it % ACC_STAGES;
+      const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tempty_bar[acc], aph ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * HALVES * BLOCK_N;
       for (int kb = 0; kb < nkb; ++kb, ++kc) {
         const uint32_t stage = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1u;
@@ -149,8 +158,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128-B swizzle span: +2 in 16-B units
-            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            // advance 16 bf16 (32 B) along K inside the 128-B swizzle span: +2 in 16-B units;
+            // the second M=128 half of a 256-row A tile starts 128 rows * 128 B = 16 KB further (+1024 units)
+#pragma unroll
+            for (int hf = 0; hf < HALVES; ++hf)
+              umma_bf16(d_tmem + hf * BLOCK_N, a_desc + 1024u * hf + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);
@@ -165,65 +177,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
-      const uint32_t acc = it & 1u;
-      const uint32_t aph = (it >> 1) & 1u;
+      const uint32_t acc = it % ACC_STAGES;
+      const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      const int row = m_tile * GEMM_BM + q * 32 + lane;
       const int n0 = n_tile * BLOCK_N;
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-      const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {
-          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        if (!row_ok) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = n0 + c * 32 + j * 8;
-          if (col >= p.N) continue;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]) * p.alpha;
-          if (p.bias != nullptr) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      for (int hf = 0; hf < HALVES; ++hf) {
+        const int row = m_tile * BLOCK_M + hf * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (acc * HALVES + hf) * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (hf == HALVES - 1 && c == BLOCK_N / 32 - 1) {
+            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          if (p.act == 1) {
+          if (!row_ok) continue;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-          } else if (p.act == 2) {
+          for (int j = 0; j < 4; ++j) {
+            const int col = n0 + c * 32 + j * 8;
+            if (col >= p.N) continue;
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-          }
-          if (p.residual != nullptr) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-            const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                         r3 = unpack_bf16x2(rr.w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-            uint4 pk;
-            pk.x = pack_bf16x2(v[0], v[1]);
-            pk.y = pack_bf16x2(v[2], v[3]);
-            pk.z = pack_bf16x2(v[4], v[5]);
-            pk.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(o) = pk;
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]) * p.alpha;
+            if (p.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
+            if (p.residual != nullptr) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                           r3 = unpack_bf16x2(rr.w);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]);
+              pk.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(o) = pk;
+            }
           }
         }
       }
@@ -281,12 +296,13 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t k, 
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_M, int BLOCK_N>
 static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_M, BLOCK_N>;
+  constexpr int GEMM_BM = BLOCK_M;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_M, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -322,32 +338,37 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   p.alpha = g->alpha;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  gemm_tcgen05_kernel<BLOCK_M, BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   SLAM_LAUNCH_CHECK("slam_gemm_bf16");
   return 0;
 }
 
-static int pick_block_n(int m, int n) {
-  if (n <= 64) return 64;
-  if (n < 192) return 128;
-  // cost = waves x tile width x per-flop penalty.  Measured on B200 (profiles/r01_gemm_bench_v0.json): BLOCK_N=128 tiles are
-  // shared-memory-bandwidth bound (~0.65x the per-flop rate of 256); 192 re-reads A slightly more often than 256 but fixes
-  // the wave quantisation of the N=4096 / 6144 decoder GEMMs at M=1600 (286 tiles = 1.93 waves instead of 208 = 1.41).
+// Tile choice by a cost model fitted to B200 measurements (profiles/r01_gemm_bench_*.json): per k-block a CTA needs
+// max(MMA cycles, tile bytes / ~60 B/clk) cycles — the second term (bytes one SM can keep in flight from L2) dominates for
+// 128-row tiles — and the launch costs ceil(tiles / SMs) waves of that.  Returns BLOCK_M * 1000 + BLOCK_N.
+static int pick_tile(int m, int n) {
+  if (n <= 64) return 128 * 1000 + 64;
   const int sms = num_sms();
-  const int64_t mt = ceil_div(m, GEMM_BM);
-  const int cands[3] = {256, 192, 128};
-  const double pen[3] = {1.0, 1.04, 1.5};
+  const int bms[6] = {256, 256, 128, 128, 128, 256};
+  const int bns[6] = {256, 192, 256, 192, 128, 128};
   double best = 1e30;
-  int best_bn = 256;
-  for (int i = 0; i < 3; ++i) {
-    if (cands[i] > n && i < 2) continue;
-    const double c = static_cast<double>(ceil_div(mt * ceil_div(n, cands[i]), sms)) * cands[i] * pen[i];
-    if (c < best) {
-      best = c;
-      best_bn = cands[i];
+  int best_tile = 128 * 1000 + 128;
+  for (int i = 0; i < 6; ++i) {
+    const int bm = bms[i], bn = bns[i];
+    if (bn > n && bn != 128) continue;
+    const double mma = (bm / 128) * 128.0 * bn * 64.0 / 4096.0;       // MMA cycles per k-block (4096 bf16 MAC/clk/SM)
+    const double bytes = (bm + bn) * 64.0 * 2.0 / 60.0;
+    const double per_kb = mma > bytes ? mma : bytes;
+    const int64_t tiles = ceil_div(m, bm) * ceil_div(n, bn);
+    const double waves = static_cast<double>(ceil_div(tiles, sms));
+    // BLOCK_M=256 tiles have a single accumulator stage: the epilogue (~1.5 us) is exposed once per tile
+    const double cost = waves * (per_kb + (bm == 256 ? 40.0 : 0.0));
+    if (cost < best) {
+      best = cost;
+      best_tile = bm * 1000 + bn;
     }
   }
-  return best_bn;
+  return best_tile;
 }
 
 }  // namespace slam
@@ -364,13 +385,17 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   SLAM_CHECK_ARG(g->bias == nullptr || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int bn = g->block_n;
-  if (bn == 0) bn = pick_block_n(g->m, g->n);
-  switch (bn) {
-    case 256: return launch_gemm<256>(g, st);
-    case 192: return launch_gemm<192>(g, st);
-    case 128: return launch_gemm<128>(g, st);
-    case 64: return launch_gemm<64>(g, st);
-    default: set_error("gemm: unsupported block_n %d", bn); return -1;
+  int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
+  if (tile == 0) tile = pick_tile(g->m, g->n);
+  if (tile < 1000) tile += 128 * 1000;
+  switch (tile) {
+    case 128256: return launch_gemm<128, 256>(g, st);
+    case 128192: return launch_gemm<128, 192>(g, st);
+    case 128128: return launch_gemm<128, 128>(g, st);
+    case 128064: return launch_gemm<128, 64>(g, st);
+    case 256256: return launch_gemm<256, 256>(g, st);
+    case 256192: return launch_gemm<256, 192>(g, st);
+    case 256128: return launch_gemm<256, 128>(g, st);
+    default: set_error("gemm: unsupported tile %d", tile); return -1;
   }
 }

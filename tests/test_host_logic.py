@@ -268,3 +268,25 @@ def test_reference_arm_only_rank0_works(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("LOCAL_RANK", "1")
     bench.run_reference(types.SimpleNamespace(workload="c3", steps=1, warmup=0, gpus=2))
     assert capsys.readouterr().out == ""                            # non-zero ranks exit without work or output
+
+
+# ------------------------------------------------------------------------------------------------- reference recipe files, unchanged
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/asr_librispeech"), reason="reference tree not present (GPU box)")
+def test_reference_recipe_files_import_unchanged_against_the_mirror(monkeypatch):
+    """examples/asr_librispeech/{finetune_asr.py, asr_config.py, model/slam_model_asr.py} import slam_llm by name; they must
+    load against src/slam_llm without modification (hydra / omegaconf via the offline shims)."""
+    rec = "/root/reference/examples/asr_librispeech"
+    monkeypatch.syspath_prepend(rec)
+    from slam_llm.utils.dataset_utils import load_module_from_py_file
+    asr_config = load_module_from_py_file(os.path.join(rec, "asr_config.py"))
+    sys.modules["asr_config"] = asr_config
+    ft = load_module_from_py_file(os.path.join(rec, "finetune_asr.py"))
+    cfg = OmegaConf.merge(ft.RunConfig(), OmegaConf.from_dotlist(["++train_config.use_peft=true", "++model_config.encoder_name=whisper"]))
+    assert cfg.train_config.peft_config.r == 8 and cfg.model_config.encoder_projector == "linear" and cfg.dataset_config.mel_size == 80
+    assert cfg.dataset_config.file == "src/slam_llm/datasets/speech_dataset.py:get_speech_dataset"
+    assert os.path.isfile(os.path.join(ROOT, cfg.dataset_config.file.split(":")[0]))      # default path resolves from the repo root
+    model_mod = load_module_from_py_file(os.path.join(rec, "model", "slam_model_asr.py"))
+    import slam_llm.models.slam_model as sm
+    assert issubclass(model_mod.slam_model_asr, sm.slam_model) and callable(model_mod.model_factory)
+    from slam_llm.pipeline.finetune import main
+    assert ft.train is main

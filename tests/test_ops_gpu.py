@@ -43,6 +43,7 @@ def cos_sim(a, b):
     (1600, 4096, 4096, 0), (300, 384, 1920, 0), (308, 2048, 512, 256),
     (1, 64, 64, 64), (257, 1280, 1280, 128), (1200, 6144, 4096, 256), (77, 5120, 240, 0),
     (1600, 4096, 4096, 192), (300, 200, 512, 192), (1600, 6144, 4096, 192),
+    (1600, 4096, 4096, 256256), (300, 384, 1920, 256192), (6000, 1280, 1280, 256256), (257, 520, 640, 256128), (129, 256, 64, 256256),
 ])
 def test_gemm_plain(ops, M, N, K, bn):
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
@@ -70,7 +71,7 @@ def test_gemm_epilogue(ops, act):
     a, b = rnd(M, K, scale=0.5, seed=3), rnd(N, K, scale=0.1, seed=4)
     bias = rnd(N, dtype=F32, seed=5)
     res = rnd(M, N, seed=6)
-    out = ops.gemm(a, b, bias=bias, residual=res, act=act, alpha=0.5)
+    out = ops.gemm(a, b, bias=bias, residual=res, act=act, alpha=0.5, block_n=(0, 256256, 128192)[act])
     z = 0.5 * (a.float() @ b.float().t()) + bias
     if act == 1:
         z = torch.nn.functional.gelu(z)
@@ -80,12 +81,13 @@ def test_gemm_epilogue(ops, act):
     assert rel_err(out, ref) < 6e-3
 
 
-def test_gemm_dual_segment_lora(ops):
+@pytest.mark.parametrize("tile", [0, 128256, 128192, 256256, 256192])
+def test_gemm_dual_segment_lora(ops, tile):
     # y = x W^T + (x A^T)(s B)^T accumulated in one TMEM tile
     M, N, K, R = 1600, 6144, 4096, 64
     x, w = rnd(M, K, seed=8), rnd(N, K, scale=0.02, seed=9)
     t, bs = rnd(M, R, seed=10), rnd(N, R, scale=0.05, seed=11)
-    out = ops.gemm(x, w, a2=t, b2=bs)
+    out = ops.gemm(x, w, a2=t, b2=bs, block_n=tile)
     ref = x.float() @ w.float().t() + t.float() @ bs.float().t()
     assert rel_err(out, ref) < 6e-3
     only_base = ops.gemm(x, w)
