@@ -162,6 +162,8 @@ int slam_cast_bf16_to_f32(const void* x_bf16, float* y, int64_t n, void* stream)
 /* y[C,R] = x[R,C]^T (bf16) */
 int slam_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
                         void* stream);
+/* dst[b][j][i] = src[b][i][j] (f32): Conv1d weight-gradient layout [co,(k,c)] -> [co,c,k] of the cov1d projector */
+int slam_transpose_f32_batched(const float* src, float* dst, int32_t batch, int32_t rows, int32_t cols, void* stream);
 /* y[i,:] = x[idx[i],:]  /  y[idx[i],:] = x[i,:] (rows of d bf16; idx i32) */
 int slam_gather_rows(const void* x_bf16, const int32_t* idx, void* y_bf16, int32_t n_idx, int32_t d,
                      void* stream);

@@ -79,9 +79,12 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long 
 }
 
 // ------------------------------------------------------------------------------------------- forward
-template <int DH>
-__global__ void __launch_bounds__(128, DH == 64 ? 4 : 2) attn_fwd_kernel(const AttnP p) {
-  constexpr int BM = 64, BN = 64, PITCH = DH + 8;
+// MT = 16-row query tiles per warp.  MT = 2 (128 query rows per CTA) re-uses every K/V fragment read from shared memory for
+// two MMAs, halving the ldmatrix traffic per flop (the limiter of mma.sync attention at dh = 64); dh = 128 keeps MT = 1
+// (the fp32 output tile alone is 64 registers per 16 rows).
+template <int DH, int MT>
+__global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_kernel(const AttnP p) {
+  constexpr int BM = 64 * MT, BN = 64, PITCH = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
   bf16* sKb = sQ + BM * PITCH;                 // 2 stages of K
@@ -111,13 +114,18 @@ __global__ void __launch_bounds__(128, DH == 64 ? 4 : 2) attn_fwd_kernel(const A
     sMask[col] = col < p.sk ? mk[col] : 0;
   }
 
-  uint32_t qf[DH / 16][4];
-  float o[DH / 8][4];
+  uint32_t qf[MT][DH / 16][4];
+  float o[MT][DH / 8][4];
+  float mrow[MT][2], lrow[MT][2];
 #pragma unroll
-  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
-  float mrow[2] = {-CUDART_INF_F, -CUDART_INF_F};
-  float lrow[2] = {0.0f, 0.0f};
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) o[mt][i][0] = o[mt][i][1] = o[mt][i][2] = o[mt][i][3] = 0.0f;
+    mrow[mt][0] = mrow[mt][1] = -CUDART_INF_F;
+    lrow[mt][0] = lrow[mt][1] = 0.0f;
+  }
   const float scale_log2 = p.scale * kLog2e;
+  const int wrow = q0 + warp * 16 * MT;    // first query row of this warp
 
   for (int t = 0; t < n_tiles; ++t) {
     const int n0 = t * BN;
@@ -132,86 +140,102 @@ __global__ void __launch_bounds__(128, DH == 64 ? 4 : 2) attn_fwd_kernel(const A
     }
     if (t == 0) {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ks * 16 + (lane >> 4) * 8);
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          ldsm_x4(qf[mt][ks], sQ + (warp * 16 * MT + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + ks * 16 + (lane >> 4) * 8);
     }
     const bf16* sK = sKb + (t & 1) * BN * PITCH;
     const bf16* sV = sVb + (t & 1) * BN * PITCH;
     const uint8_t* sM = sMask + (t & 1) * BN;
 
-    float s[BN / 8][4];
+    float s[MT][BN / 8][4];
 #pragma unroll
-    for (int i = 0; i < BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < BN / 8; ++i) s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.0f;
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
 #pragma unroll
       for (int nb2 = 0; nb2 < BN / 16; ++nb2) {
         uint32_t kb[4];
         ldsm_x4(kb, sK + (nb2 * 16 + (lane & 7) + (lane >> 4) * 8) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma16816(s[2 * nb2], qf[ks], kb[0], kb[1]);
-        mma16816(s[2 * nb2 + 1], qf[ks], kb[2], kb[3]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma16816(s[mt][2 * nb2], qf[mt][ks], kb[0], kb[1]);
+          mma16816(s[mt][2 * nb2 + 1], qf[mt][ks], kb[2], kb[3]);
+        }
       }
     }
     // scale + mask (log2 domain); only boundary / diagonal / masked tiles need the per-element test
     const bool need_mask = (n0 + BN > p.sk) || (p.causal && n0 + BN > q0) || mk != nullptr;
 #pragma unroll
-    for (int nb = 0; nb < BN / 8; ++nb) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v = s[nb][e] * scale_log2;
-        if (need_mask) {
-          const int cl = nb * 8 + 2 * (lane & 3) + (e & 1);
-          const int col = n0 + cl;
-          const int row = q0 + warp * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
-          bool ok = col < p.sk && (!p.causal || col <= row);
-          if (ok && mk != nullptr) ok = sM[cl] != 0;
-          v = ok ? v : -CUDART_INF_F;
-        }
-        s[nb][e] = v;
-      }
-    }
-    // online softmax, two rows per thread
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float mx = -CUDART_INF_F;
-#pragma unroll
-      for (int nb = 0; nb < BN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * r], s[nb][2 * r + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(mrow[r], mx);
-      const float m_safe = m_new == -CUDART_INF_F ? 0.0f : m_new;
-      const float corr = exp2f(mrow[r] - m_safe);
-      mrow[r] = m_new;
-      float rs = 0.0f;
+    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int nb = 0; nb < BN / 8; ++nb) {
-        const float p0 = exp2f(s[nb][2 * r] - m_safe);
-        const float p1 = exp2f(s[nb][2 * r + 1] - m_safe);
-        s[nb][2 * r] = p0;
-        s[nb][2 * r + 1] = p1;
-        rs += p0 + p1;
-      }
-      lrow[r] = lrow[r] * corr + rs;
 #pragma unroll
-      for (int i = 0; i < DH / 8; ++i) {
-        o[i][2 * r] *= corr;
-        o[i][2 * r + 1] *= corr;
+        for (int e = 0; e < 4; ++e) {
+          float v = s[mt][nb][e] * scale_log2;
+          if (need_mask) {
+            const int cl = nb * 8 + 2 * (lane & 3) + (e & 1);
+            const int col = n0 + cl;
+            const int row = wrow + mt * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+            bool ok = col < p.sk && (!p.causal || col <= row);
+            if (ok && mk != nullptr) ok = sM[cl] != 0;
+            v = ok ? v : -CUDART_INF_F;
+          }
+          s[mt][nb][e] = v;
+        }
+      }
+      // online softmax, two rows per thread and m-tile
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float mx = -CUDART_INF_F;
+#pragma unroll
+        for (int nb = 0; nb < BN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[mt][nb][2 * r], s[mt][nb][2 * r + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(mrow[mt][r], mx);
+        const float m_safe = m_new == -CUDART_INF_F ? 0.0f : m_new;
+        const float corr = exp2f(mrow[mt][r] - m_safe);
+        mrow[mt][r] = m_new;
+        float rs = 0.0f;
+#pragma unroll
+        for (int nb = 0; nb < BN / 8; ++nb) {
+          const float p0 = exp2f(s[mt][nb][2 * r] - m_safe);
+          const float p1 = exp2f(s[mt][nb][2 * r + 1] - m_safe);
+          s[mt][nb][2 * r] = p0;
+          s[mt][nb][2 * r + 1] = p1;
+          rs += p0 + p1;
+        }
+        lrow[mt][r] = lrow[mt][r] * corr + rs;
+#pragma unroll
+        for (int i = 0; i < DH / 8; ++i) {
+          o[mt][i][2 * r] *= corr;
+          o[mt][i][2 * r + 1] *= corr;
+        }
       }
     }
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < BN / 16; ++kk) {
-      uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        a[mt][0] = pack_bf16x2(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+        a[mt][1] = pack_bf16x2(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+        a[mt][2] = pack_bf16x2(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+        a[mt][3] = pack_bf16x2(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+      }
 #pragma unroll
       for (int nb2 = 0; nb2 < DH / 16; ++nb2) {
         uint32_t vb[4];
         ldsm_x4_t(vb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + nb2 * 16 + (lane >> 4) * 8);
-        mma16816(o[2 * nb2], a, vb[0], vb[1]);
-        mma16816(o[2 * nb2 + 1], a, vb[2], vb[3]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma16816(o[mt][2 * nb2], a[mt], vb[0], vb[1]);
+          mma16816(o[mt][2 * nb2 + 1], a[mt], vb[2], vb[3]);
+        }
       }
     }
     if (t + 1 < n_tiles && mk != nullptr && threadIdx.x < BN) sMask[((t + 1) & 1) * BN + threadIdx.x] = mreg;
@@ -219,23 +243,26 @@ __global__ void __launch_bounds__(128, DH == 64 ? 4 : 2) attn_fwd_kernel(const A
 
   // finalize
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    float l = lrow[r];
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
-    const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-    if (row < p.sq) {
-      bf16* orow = p.out + (static_cast<long long>(b) * p.sq + row) * p.ldo + h * DH;
+  for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-      for (int i = 0; i < DH / 8; ++i) {
-        const uint32_t pk = pack_bf16x2(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
-        *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * (lane & 3)) = pk;
-      }
-      if (p.lse != nullptr && (lane & 3) == 0) {
-        // fully masked row: lse = 0 keeps exp(s - lse) = 0 in the backward (s = -inf there)
-        const float lse = l > 0.0f ? mrow[r] * kLn2 + logf(l) : 0.0f;
-        p.lse[(static_cast<long long>(b) * p.hq + h) * p.sq + row] = lse;
+    for (int r = 0; r < 2; ++r) {
+      float l = lrow[mt][r];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const int row = wrow + mt * 16 + (lane >> 2) + r * 8;
+      const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+      if (row < p.sq) {
+        bf16* orow = p.out + (static_cast<long long>(b) * p.sq + row) * p.ldo + h * DH;
+#pragma unroll
+        for (int i = 0; i < DH / 8; ++i) {
+          const uint32_t pk = pack_bf16x2(o[mt][i][2 * r] * inv, o[mt][i][2 * r + 1] * inv);
+          *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * (lane & 3)) = pk;
+        }
+        if (p.lse != nullptr && (lane & 3) == 0) {
+          // fully masked row: lse = 0 keeps exp(s - lse) = 0 in the backward (s = -inf there)
+          const float lse = l > 0.0f ? mrow[mt][r] * kLn2 + logf(l) : 0.0f;
+          p.lse[(static_cast<long long>(b) * p.hq + h) * p.sq + row] = lse;
+        }
       }
     }
   }
@@ -506,16 +533,16 @@ static int fill_params(const slam_attn_args* a, AttnP& p, bool bwd) {
   return 0;
 }
 
-template <int DH>
+template <int DH, int MT>
 static int launch_fwd(const AttnP& p, cudaStream_t st) {
-  constexpr int SMEM = 5 * 64 * (DH + 8) * 2 + 128;
+  constexpr int SMEM = (4 + MT) * 64 * (DH + 8) * 2 + 128;
   static bool set = false;
   if (!set) {
-    cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<DH, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     set = true;
   }
-  dim3 grid(static_cast<unsigned>(ceil_div(p.sq, 64)), p.hq, p.batch);
-  attn_fwd_kernel<DH><<<grid, 128, SMEM, st>>>(p);
+  dim3 grid(static_cast<unsigned>(ceil_div(p.sq, 64 * MT)), p.hq, p.batch);
+  attn_fwd_kernel<DH, MT><<<grid, 128, SMEM, st>>>(p);
   SLAM_LAUNCH_CHECK("slam_attn_fwd");
   return 0;
 }
@@ -541,7 +568,8 @@ extern "C" int slam_attn_fwd(const slam_attn_args* a, void* stream) {
   int rc = fill_params(a, p, false);
   if (rc != 0) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return a->dh == 64 ? launch_fwd<64>(p, st) : launch_fwd<128>(p, st);
+  if (a->dh == 128) return launch_fwd<128, 1>(p, st);
+  return a->sq >= 256 ? launch_fwd<64, 2>(p, st) : launch_fwd<64, 1>(p, st);
 }
 
 extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {

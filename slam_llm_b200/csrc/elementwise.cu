@@ -122,6 +122,25 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, b
   }
 }
 
+// batched f32 transpose: dst[b][j][i] = src[b][i][j]   (conv1d weight-gradient layout change, small)
+__global__ void transpose_f32_batched_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + static_cast<int64_t>(b) * rows * cols;
+  float* d = dst + static_cast<int64_t>(b) * rows * cols;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? s[static_cast<int64_t>(r) * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) d[static_cast<int64_t>(c) * rows + r] = tile[tx][i];
+  }
+}
+
 // ---------------------------------------------------------------- row gather / scatter (d % 8 == 0)
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ idx, bf16* __restrict__ y, int n_idx, int d, int scatter) {
   const int i = blockIdx.x;
@@ -531,6 +550,13 @@ int slam_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_
   dim3 grid(static_cast<unsigned>(ceil_div(cols, 64)), static_cast<unsigned>(ceil_div(rows, 64)));
   transpose_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, rows, cols);
   SLAM_LAUNCH_CHECK("slam_transpose_bf16");
+  return 0;
+}
+int slam_transpose_f32_batched(const float* src, float* dst, int32_t batch, int32_t rows, int32_t cols, void* stream) {
+  SLAM_CHECK_ARG(batch > 0 && rows > 0 && cols > 0 && batch <= 65535, "transpose_f32_batched: bad shape");
+  dim3 grid(static_cast<unsigned>(ceil_div(cols, 32)), static_cast<unsigned>(ceil_div(rows, 32)), batch);
+  transpose_f32_batched_kernel<<<grid, 256, 0, ST(stream)>>>(src, dst, rows, cols);
+  SLAM_LAUNCH_CHECK("slam_transpose_f32_batched");
   return 0;
 }
 int slam_gather_rows(const void* x, const int32_t* idx, void* y, int32_t n_idx, int32_t d, void* stream) {

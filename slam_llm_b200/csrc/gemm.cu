@@ -53,7 +53,9 @@ struct GemmCfg {
   static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int EPI_PITCH = 36;                                    // floats per staged row (32 + 4 pad: conflict-free)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                 // one 32x32 fp32 chunk per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
@@ -76,6 +78,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,11 +185,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const int n0 = n_tile * BLOCK_N;
+      // Each chunk of 32 accumulator columns goes TMEM -> registers (thread = row) -> a padded shared-memory tile ->
+      // registers again with (8 rows x 4 column-pieces) per warp instruction, so that global stores and residual loads
+      // touch whole 32-byte sectors (64 B of bf16 per row) instead of one 16-byte piece of 32 different rows.
+      float* stg = epi_stage + q * (32 * Cfg::EPI_PITCH);
+      const int piece = lane & 3;
 #pragma unroll 1
       for (int hf = 0; hf < HALVES; ++hf) {
-        const int row = m_tile * BLOCK_M + hf * 128 + q * 32 + lane;
+        const int row_base = m_tile * BLOCK_M + hf * 128 + q * 32;
         const uint32_t taddr = tmem_base + (acc * HALVES + hf) * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-        const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t r[32];
@@ -198,14 +205,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          if (!row_ok) continue;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = n0 + c * 32 + j * 8;
-            if (col >= p.N) continue;
-            float v[8];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const int col = n0 + c * 32 + piece * 8;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]) * p.alpha;
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const int row = row_base + rr;
+            if (row >= p.M || col >= p.N) continue;
+            const float4 x0 = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_PITCH + piece * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_PITCH + piece * 8 + 4);
+            float v[8] = {x0.x * p.alpha, x0.y * p.alpha, x0.z * p.alpha, x0.w * p.alpha,
+                          x1.x * p.alpha, x1.y * p.alpha, x1.z * p.alpha, x1.w * p.alpha};
             if (p.bias != nullptr) {
               const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
               const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
@@ -220,9 +233,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
             }
             if (p.residual != nullptr) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                           r3 = unpack_bf16x2(rr.w);
+              const uint4 rsd = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+              const float2 r0 = unpack_bf16x2(rsd.x), r1 = unpack_bf16x2(rsd.y), r2 = unpack_bf16x2(rsd.z),
+                           r3 = unpack_bf16x2(rsd.w);
               v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
               v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
             }
@@ -240,6 +253,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               *reinterpret_cast<uint4*>(o) = pk;
             }
           }
+          __syncwarp();
         }
       }
     }
@@ -343,32 +357,31 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   return 0;
 }
 
-// Tile choice by a cost model fitted to B200 measurements (profiles/r01_gemm_bench_*.json): per k-block a CTA needs
-// max(MMA cycles, tile bytes / ~60 B/clk) cycles — the second term (bytes one SM can keep in flight from L2) dominates for
-// 128-row tiles — and the launch costs ceil(tiles / SMs) waves of that.  Returns BLOCK_M * 1000 + BLOCK_N.
-static int pick_tile(int m, int n) {
+// Tile choice fitted to B200 measurements (profiles/r01_gemm_bench_v2.json).  Returns BLOCK_M * 1000 + BLOCK_N.
+//  * 128-row tiles have two TMEM accumulator stages (epilogue overlaps the next tile): pick 256 vs 192 columns by wave
+//    quantisation, cost = ceil(tiles / SMs) * BLOCK_N * penalty (192 re-reads A slightly more often; 128 is smem-bound).
+//  * 256x256 tiles (two M=128 accumulators sharing each B tile) need 1/3 less L2->SM traffic per MMA cycle but expose their
+//    epilogue once per tile: they win only when the whole GEMM is a single wave and K is long enough to amortise it
+//    (down_proj, the gate/up dgrad, the encoder fc2: +8..12 %); with several waves they lose 10-20 %.
+static int pick_tile(int m, int n, int k) {
   if (n <= 64) return 128 * 1000 + 64;
+  if (n < 192) return 128 * 1000 + 128;
   const int sms = num_sms();
-  const int bms[6] = {256, 256, 128, 128, 128, 256};
-  const int bns[6] = {256, 192, 256, 192, 128, 128};
+  if (k >= 5000 && n >= 256 && ceil_div(m, 256) * ceil_div(n, 256) <= sms) return 256 * 1000 + 256;
+  const int64_t mt = ceil_div(m, 128);
+  const int cands[3] = {256, 192, 128};
+  const double pen[3] = {1.0, 1.04, 1.5};
   double best = 1e30;
-  int best_tile = 128 * 1000 + 128;
-  for (int i = 0; i < 6; ++i) {
-    const int bm = bms[i], bn = bns[i];
-    if (bn > n && bn != 128) continue;
-    const double mma = (bm / 128) * 128.0 * bn * 64.0 / 4096.0;       // MMA cycles per k-block (4096 bf16 MAC/clk/SM)
-    const double bytes = (bm + bn) * 64.0 * 2.0 / 60.0;
-    const double per_kb = mma > bytes ? mma : bytes;
-    const int64_t tiles = ceil_div(m, bm) * ceil_div(n, bn);
-    const double waves = static_cast<double>(ceil_div(tiles, sms));
-    // BLOCK_M=256 tiles have a single accumulator stage: the epilogue (~1.5 us) is exposed once per tile
-    const double cost = waves * (per_kb + (bm == 256 ? 40.0 : 0.0));
-    if (cost < best) {
-      best = cost;
-      best_tile = bm * 1000 + bn;
+  int best_bn = 256;
+  for (int i = 0; i < 3; ++i) {
+    if (cands[i] > n && i < 2) continue;
+    const double c = static_cast<double>(ceil_div(mt * ceil_div(n, cands[i]), sms)) * cands[i] * pen[i];
+    if (c < best) {
+      best = c;
+      best_bn = cands[i];
     }
   }
-  return best_tile;
+  return 128 * 1000 + best_bn;
 }
 
 }  // namespace slam
@@ -386,7 +399,7 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
-  if (tile == 0) tile = pick_tile(g->m, g->n);
+  if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2);
   if (tile < 1000) tile += 128 * 1000;
   switch (tile) {
     case 128256: return launch_gemm<128, 256>(g, st);

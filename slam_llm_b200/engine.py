@@ -168,69 +168,99 @@ class WhisperEncoderB200:
 # projector (trainable): EncoderProjectorConcat
 # =====================================================================================================
 class ProjectorB200:
+    """EncoderProjectorConcat (projector.py:5-27) and EncoderProjectorCov1d (projector.py:29-49).
+
+    Both are a chain of Linear(+ReLU) layers on the k-frame-concatenated encoder output: Conv1d(d, d, k, stride=k, pad=0) on
+    [B, d, T'] is exactly a Linear(k*d -> d) on the non-overlapping windows with the kernel re-laid-out as [co, (kk, c)]."""
     PREFIX = "encoder_projector."
 
     def __init__(self, enc: EncoderCfg, llm: LlmCfg, proj: ProjCfg, arena: TrainableArena):
-        if proj.kind != "linear":
-            raise NotImplementedError(f"projector kind {proj.kind!r}: only the concat-linear projector is on the B200 path so far")
-        self.cfg, self.k, self.d_in, self.hidden, self.d_out = proj, proj.k, enc.d * proj.k, proj.hidden, llm.d
+        self.cfg, self.k, self.d_enc, self.hidden, self.d_out = proj, proj.k, enc.d, proj.hidden, llm.d
+        self.d_in = enc.d * proj.k
         self.arena = arena
-        arena.add(self.PREFIX + "linear1.weight", (self.hidden, self.d_in))
-        arena.add(self.PREFIX + "linear1.bias", (self.hidden,))
-        arena.add(self.PREFIX + "linear2.weight", (self.d_out, self.hidden))
-        arena.add(self.PREFIX + "linear2.bias", (self.d_out,))
+        P = self.PREFIX
+        if proj.kind == "linear":
+            self.chain = [("linear1", self.hidden, self.d_in, True), ("linear2", self.d_out, self.hidden, False)]
+        elif proj.kind == "cov1d-linear":
+            arena.add(P + "conv1d.weight", (enc.d, enc.d, proj.k))
+            arena.add(P + "conv1d.bias", (enc.d,))
+            self.chain = [("conv1d", enc.d, self.d_in, True), ("linear1", self.hidden, enc.d, True), ("linear2", self.d_out, self.hidden, False)]
+        else:
+            raise NotImplementedError(f"projector kind {proj.kind!r} is not on the B200 path (q-former is out of scope)")
+        for name, out_f, in_f, _ in self.chain:
+            if name != "conv1d":
+                arena.add(P + f"{name}.weight", (out_f, in_f))
+                arena.add(P + f"{name}.bias", (out_f,))
         self.saved = None
+
+    def param_names(self) -> List[str]:
+        return [f"{name}.{sfx}" for name, _, _, _ in self.chain for sfx in ("weight", "bias")]
 
     def init_weights(self, weights: Optional[Dict[str, torch.Tensor]], seed: int = 45) -> None:
         a = self.arena
         if weights is not None:
-            for k in ("linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"):
+            for k in self.param_names():
                 a.view(self.PREFIX + k).copy_(weights[k].to(a.param.device, F32))
             return
         g = torch.Generator(device="cuda").manual_seed(seed)
-        for name, fan_in in (("linear1", self.d_in), ("linear2", self.hidden)):
-            b = 1.0 / math.sqrt(fan_in)
+        for name, _, in_f, _ in self.chain:                              # nn.Linear / nn.Conv1d default init
+            b = 1.0 / math.sqrt(in_f)
             for suffix in ("weight", "bias"):
                 v = a.view(self.PREFIX + f"{name}.{suffix}")
                 v.copy_((torch.rand(v.shape, generator=g, device="cuda") * 2 - 1) * b)
+
+    def _weight_bf16(self, name: str, out_f: int, in_f: int) -> torch.Tensor:
+        w = self.arena.view(self.PREFIX + f"{name}.weight")
+        if name != "conv1d":
+            return ops.cast_bf16(w)
+        d, k = self.d_enc, self.k                                        # [co, c, kk] -> [co, (kk, c)]
+        out = torch.empty((d, k * d), device=w.device, dtype=BF16)
+        return ops.pack2d(w, out, batch=d, rows=d, cols=k, src_bs=d * k, src_ld=k, dst_bs=k * d, dst_ld=d, transpose=True)
 
     def forward(self, enc_out: torch.Tensor, save: bool) -> torch.Tensor:
         """enc_out bf16 [B, T', d] -> bf16 [B, T'//k, D]."""
         B, Tp, d = enc_out.shape
         Ta = Tp // self.k
         if Tp % self.k:
-            enc_out = enc_out[:, : Ta * self.k].contiguous()                              # projector.py:17-19 (drop tail frames)
-        xcat = enc_out.reshape(B * Ta, self.k * d)
-        a = self.arena
-        w1 = ops.cast_bf16(a.view(self.PREFIX + "linear1.weight"))
-        w2 = ops.cast_bf16(a.view(self.PREFIX + "linear2.weight"))
-        h1 = ops.gemm(xcat, w1, bias=a.view(self.PREFIX + "linear1.bias"), act=2)
-        y = ops.gemm(h1, w2, bias=a.view(self.PREFIX + "linear2.bias"))
+            enc_out = enc_out[:, : Ta * self.k].contiguous()             # projector.py:17-19 / conv stride drops the tail frames
+        h = enc_out.reshape(B * Ta, self.k * d)
+        acts, wts = [h], []
+        for name, out_f, in_f, relu in self.chain:
+            w = self._weight_bf16(name, out_f, in_f)
+            h = ops.gemm(h, w, bias=self.arena.view(self.PREFIX + f"{name}.bias"), act=2 if relu else 0)
+            acts.append(h)
+            wts.append(w)
         if save:
-            self.saved = (xcat, h1, w2)
-        return y.view(B, Ta, self.d_out)
+            self.saved = (acts, wts)
+        return h.view(B, Ta, self.d_out)
 
     def backward(self, dy: torch.Tensor) -> None:
-        """dy bf16 [B, Ta, D]; writes grads of linear1/linear2 into the arena (encoder frozen: no dX)."""
-        xcat, h1, w2 = self.saved
+        """dy bf16 [B, Ta, D]; writes the weight/bias grads into the arena (encoder frozen: no dX)."""
+        acts, wts = self.saved
         self.saved = None
         a = self.arena
-        M = xcat.shape[0]
-        dy2 = dy.reshape(M, self.d_out)
+        M = acts[0].shape[0]
         Mp = _round_up(M, 8)
 
         def tpose(x):  # [M, C] -> [C, M] with a 16-byte aligned leading dimension
             buf = torch.zeros((x.shape[1], Mp), device=x.device, dtype=BF16) if Mp != M else torch.empty((x.shape[1], M), device=x.device, dtype=BF16)
             return ops.transpose(x, out=buf[:, :M])
 
-        dyT, h1T = tpose(dy2), tpose(h1)
-        ops.gemm(dyT, h1T, out=a.view(self.PREFIX + "linear2.weight", "grad"), out_f32=True)          # dW2 = dY^T H1
-        ops.colsum(dy2, a.view(self.PREFIX + "linear2.bias", "grad"))
-        w2T = ops.transpose(w2)                                                                          # [hidden, D]
-        dh1 = ops.gemm(dy2, w2T)                                                                         # dH1 = dY W2
-        dh1 = ops.relu_bwd(dh1, h1, out=dh1)
-        ops.gemm(tpose(dh1), tpose(xcat), out=a.view(self.PREFIX + "linear1.weight", "grad"), out_f32=True)  # dW1 = dH1^T X
-        ops.colsum(dh1, a.view(self.PREFIX + "linear1.bias", "grad"))
+        g = dy.reshape(M, self.d_out)
+        for li in range(len(self.chain) - 1, -1, -1):
+            name, out_f, in_f, relu = self.chain[li]
+            if relu:
+                g = ops.relu_bwd(g, acts[li + 1], out=g)
+            gw = a.view(self.PREFIX + f"{name}.weight", "grad")
+            if name == "conv1d":
+                tmp = torch.empty((out_f, in_f), device=g.device, dtype=F32)
+                ops.gemm(tpose(g), tpose(acts[li]), out=tmp, out_f32=True)                          # [co, (kk, c)]
+                ops.transpose_f32_batched(tmp, gw, batch=self.d_enc, rows=self.k, cols=self.d_enc)  # -> [co, c, kk]
+            else:
+                ops.gemm(tpose(g), tpose(acts[li]), out=gw, out_f32=True)                           # dW = dY^T X
+            ops.colsum(g, a.view(self.PREFIX + f"{name}.bias", "grad"))
+            if li > 0:
+                g = ops.gemm(g, ops.transpose(wts[li]))                                             # dX = dY W
 
 
 # =====================================================================================================

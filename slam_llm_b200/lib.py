@@ -79,6 +79,7 @@ _SIGS = {
     "slam_cast_f32_to_bf16": [_vp, _vp, _i64, _f32, _vp],
     "slam_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "slam_transpose_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _vp],
+    "slam_transpose_f32_batched": [_vp, _vp, _i32, _i32, _i32, _vp],
     "slam_gather_rows": [_vp, _vp, _vp, _i32, _i32, _vp],
     "slam_scatter_rows": [_vp, _vp, _vp, _i32, _i32, _vp],
     "slam_relu_bwd": [_vp, _vp, _vp, _i64, _vp],

@@ -348,6 +348,14 @@ def transpose(x, out=None):
     return out
 
 
+def transpose_f32_batched(src, dst, batch: int, rows: int, cols: int):
+    """dst[b][j][i] = src[b][i][j] on contiguous f32 buffers."""
+    _req(src, F32, "transpose_f32_batched.src"); _req(dst, F32, "transpose_f32_batched.dst")
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel() == batch * rows * cols
+    _l.check(_l.load().slam_transpose_f32_batched(src.data_ptr(), dst.data_ptr(), batch, rows, cols, _stream()), "slam_transpose_f32_batched")
+    return dst
+
+
 def gather_rows(x, idx, out=None):
     _req(x, BF16, "gather_rows")
     assert idx.dtype == torch.int32 and x.is_contiguous()

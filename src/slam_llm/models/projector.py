@@ -5,6 +5,25 @@ import torch
 import torch.nn as nn
 
 
+def _bind(module, engine_projector, arena, names) -> None:
+    """Move the parameters into the flat trainable arena (the new nn.Parameters are views of arena.param)."""
+    pre = engine_projector.PREFIX
+    for name in names:
+        mod = getattr(module, name)
+        for suffix in ("weight", "bias"):
+            view = arena.view(f"{pre}{name}.{suffix}")
+            old = getattr(mod, suffix)
+            view.copy_(old.data.to(view.device, view.dtype))
+            mod._parameters[suffix] = nn.Parameter(view, requires_grad=old.requires_grad)
+    module._b200 = engine_projector
+
+
+def _forward(module, x):
+    if module._b200 is None:
+        raise RuntimeError(f"{type(module).__name__} is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
+    return module._b200.forward(x.to(torch.bfloat16).contiguous(), save=torch.is_grad_enabled())
+
+
 class EncoderProjectorConcat(nn.Module):
     """concat k frames -> Linear(k*d, 2048) -> ReLU -> Linear(2048, llm_dim)   (projector.py:5-27)."""
 
@@ -18,29 +37,36 @@ class EncoderProjectorConcat(nn.Module):
         self.linear2 = nn.Linear(2048, config.llm_dim)
         self._b200 = None  # slam_llm_b200.engine.ProjectorB200 after binding
 
+    kind = "linear"
+
     def bind(self, engine_projector, arena) -> None:
-        """Move the four parameters into the flat trainable arena (views share storage with arena.param)."""
-        pre = engine_projector.PREFIX
-        for mod, name in ((self.linear1, "linear1"), (self.linear2, "linear2")):
-            for suffix in ("weight", "bias"):
-                view = arena.view(f"{pre}{name}.{suffix}")
-                view.copy_(getattr(mod, suffix).data.to(view.device, view.dtype))
-                old = getattr(mod, suffix)
-                mod._parameters[suffix] = nn.Parameter(view, requires_grad=old.requires_grad)
-        self._b200 = engine_projector
+        _bind(self, engine_projector, arena, ("linear1", "linear2"))
 
     def forward(self, x):
-        if self._b200 is None:
-            raise RuntimeError("EncoderProjectorConcat is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
-        return self._b200.forward(x.to(torch.bfloat16).contiguous(), save=torch.is_grad_enabled())
+        return _forward(self, x)
 
 
 class EncoderProjectorCov1d(nn.Module):
     """Conv1d(d, d, k, stride k) -> ReLU -> Linear(d, 2048) -> ReLU -> Linear(2048, llm_dim)   (projector.py:29-49)."""
+    kind = "cov1d-linear"
 
     def __init__(self, config):
         super().__init__()
-        raise NotImplementedError("cov1d-linear projector: not yet on the B200 path (SURVEY.md §8a a3 alt; planned next)")
+        self.k = config.encoder_projector_ds_rate
+        self.encoder_dim = config.encoder_dim
+        self.llm_dim = config.llm_dim
+        self.conv1d = nn.Conv1d(in_channels=self.encoder_dim, out_channels=self.encoder_dim, kernel_size=self.k, stride=self.k, padding=0)
+        self.linear1 = nn.Linear(self.encoder_dim, 2048)
+        self.relu1 = nn.ReLU()
+        self.linear2 = nn.Linear(2048, self.llm_dim)
+        self.relu2 = nn.ReLU()
+        self._b200 = None
+
+    def bind(self, engine_projector, arena) -> None:
+        _bind(self, engine_projector, arena, ("conv1d", "linear1", "linear2"))
+
+    def forward(self, x):
+        return _forward(self, x)
 
 
 class EncoderProjectorQFormer(nn.Module):

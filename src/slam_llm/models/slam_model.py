@@ -135,7 +135,7 @@ class LlamaB200ForCausalLM(nn.Module):
         super().__init__()
         self.cfg, self.llm_path, self.lora_cfg, self.use_peft = cfg, llm_path, lora_cfg if use_peft else None, use_peft
         self.b200: Optional[LlamaLoRAB200] = None
-        self._step = None
+        object.__setattr__(self, "_step", None)
         D, Dkv, F, V, L = cfg.d, cfg.dkv, cfg.ffn, cfg.vocab, cfg.layers
         self.num_frozen_params = 2 * V * D + L * (2 * D * D + 2 * D * Dkv + 3 * D * F + 2 * D) + D
 
@@ -259,7 +259,7 @@ class slam_model(nn.Module):
             raise NotImplementedError("the B200 step needs a Whisper encoder, a linear projector and a Llama-architecture LLM")
         device = torch.device("cuda", torch.cuda.current_device())
         arena = TrainableArena()
-        proj_cfg = ProjCfg("linear", encoder_projector.k, encoder_projector.linear1.out_features)
+        proj_cfg = ProjCfg(encoder_projector.kind, encoder_projector.k, encoder_projector.linear1.out_features)
         eng_proj = ProjectorB200(encoder.b200.cfg, llm.cfg, proj_cfg, arena)
         llm.bind(arena, device)
         arena.finalize(device)
@@ -267,7 +267,7 @@ class slam_model(nn.Module):
         llm.b200.init_lora(None)                                    # peft init: A kaiming-uniform, B zeros
         llm.register_views(arena)
         self.b200 = SlamStepB200.from_parts(encoder.b200, eng_proj, llm.b200, arena, device)
-        llm._step = self
+        object.__setattr__(llm, "_step", self)       # plain attribute: registering the parent as a sub-module would create a cycle
         arena.param.requires_grad_(True)
         self._grad_views_set = False
         self.ddp_world_size = 1

@@ -50,6 +50,9 @@ CASES = {
     # dh = 128 decoder (Llama-3 head shape), GQA 4:1, LoRA on all seven linears (aispeech_asr style), 128-mel encoder
     "dh128_all_lora": dict(enc=so.EncoderCfg(128, 1500, 192, 3, 2), llm=so.LlmCfg(1024, 512, 3, 4, 1, 768, 500000.0, 1e-5),
                            lora=so.LoraCfg(16, 32, so.LLM_LINEARS), proj=so.ProjCfg("linear", 5, 256), B=3, n=48000, left=[2, 0, 5]),
+    # cov1d-linear projector (EncoderProjectorCov1d), no LoRA on k: plain q,v
+    "cov1d_proj": dict(enc=so.EncoderCfg(80, 1500, 128, 2, 1), llm=so.LlmCfg(512, 256, 2, 4, 4, 512, 10000.0, 1e-5),
+                       lora=so.LoraCfg(8, 16, ("q_proj", "v_proj")), proj=so.ProjCfg("cov1d-linear", 5, 128), B=2, n=40000, left=[0, 1]),
 }
 
 
@@ -91,7 +94,7 @@ def test_step_matches_oracle(name):
     eng.optimizer_step(1e-3, 0.01)
     after = eng.trainable_state()
     new_ref = om.trainable()
-    for k in ("encoder_projector.linear2.weight", "encoder_projector.linear1.bias"):
+    for k in ("encoder_projector.linear2.weight", "encoder_projector.linear1.bias") + (("encoder_projector.conv1d.weight",) if c["proj"].kind != "linear" else ()):
         upd, upd_ref = (after[k] - before[k]).cpu(), new_ref[k].detach() - before[k].cpu()
         assert cosine(upd, upd_ref) > 0.98, (k, cosine(upd, upd_ref))
 
