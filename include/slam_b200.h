@@ -67,13 +67,16 @@ int slam_wgrad_thin(const void* a_bf16, int64_t lda, int32_t p, const void* b_bf
 /* ---------------------------------------------------------------------------------------------
  * a1  log-mel front end.  whisper.pad_or_trim + whisper.log_mel_spectrogram(...).permute(1,0)
  *     as called at datasets/speech_dataset.py:101-103.
- *   wav      f32 [B, n_samples]  (already padded/trimmed; n_frames = n_samples/160)
+ *   wav      f32 [B, n_samples]  (padded/trimmed; n_frames = n_samples/160)
+ *   lengths  i32 [B] real sample counts or NULL (= all n_samples).  With lengths, utterance b is transformed as if it had
+ *            lengths[b] samples (reflect padding at ITS end, max over ITS frames) and its mel frames >= lengths[b]/160 are
+ *            zero — the reference pads the mel, not the audio, in the dynamic-frame collator (speech_dataset_large.py:196-199)
  *   filters_t f32 [201, n_mels]  (slaney mel filterbank, TRANSPOSED so mel is the contiguous axis)
  *   out      f32 [B, n_frames, n_mels]
  *   scratch  f32 [B]  per-utterance running max (written by the kernel)
  * -------------------------------------------------------------------------------------------*/
-int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, const float* filters_t,
-                int32_t n_mels, float* out, float* scratch_max, void* stream);
+int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, const int32_t* lengths,
+                const float* filters_t, int32_t n_mels, float* out, float* scratch_max, void* stream);
 
 /* a2  Whisper conv stem helpers (models/encoder.py:18-24).  Time-major activations.
  *   im2col for Conv1d(k=3, pad=1, stride s): x[B,T,C] (f32 or bf16) -> col bf16 [B*T_out, ldk]

@@ -569,7 +569,12 @@ extern "C" int slam_attn_fwd(const slam_attn_args* a, void* stream) {
   if (rc != 0) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dh == 128) return launch_fwd<128, 1>(p, st);
-  return a->sq >= 256 ? launch_fwd<64, 2>(p, st) : launch_fwd<64, 1>(p, st);
+  // MT = 2 (32 rows per warp) measured SLOWER on B200 (324 us vs 261 us per whisper-large-v3 layer: 255 registers, 8 warps/SM);
+  // it stays instantiated for experiments behind SLAM_ATTN_MT2.
+#ifdef SLAM_ATTN_MT2
+  if (a->sq >= 256) return launch_fwd<64, 2>(p, st);
+#endif
+  return launch_fwd<64, 1>(p, st);
 }
 
 extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {

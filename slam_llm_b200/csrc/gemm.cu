@@ -49,7 +49,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+#ifdef SLAM_STAGES_CAP
+  static constexpr int STAGES = STAGES_RAW > SLAM_STAGES_CAP ? SLAM_STAGES_CAP : STAGES_RAW;   // experiment: latency- vs bandwidth-bound
+#else
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+#endif
   static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
@@ -367,7 +371,8 @@ static int pick_tile(int m, int n, int k) {
   if (n <= 64) return 128 * 1000 + 64;
   if (n < 192) return 128 * 1000 + 128;
   const int sms = num_sms();
-  if (k >= 5000 && n >= 256 && ceil_div(m, 256) * ceil_div(n, 256) <= sms) return 256 * 1000 + 256;
+  const int64_t t256 = ceil_div(m, 256) * ceil_div(n, 256);
+  if (k >= 5000 && n >= 256 && t256 <= sms && t256 * 10 >= sms * 6) return 256 * 1000 + 256;   // one well-filled wave
   const int64_t mt = ceil_div(m, 128);
   const int cands[3] = {256, 192, 128};
   const double pen[3] = {1.0, 1.04, 1.5};

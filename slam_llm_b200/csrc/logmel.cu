@@ -32,8 +32,8 @@ __global__ void logmel_init_kernel(float* scratch, int batch) {
   if (i < batch) reinterpret_cast<int*>(scratch)[i] = float_key(-CUDART_INF_F);
 }
 
-__global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, const float* __restrict__ filt_t,
-                                                     int n_mels, float* __restrict__ out, float* __restrict__ scratch) {
+__global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ wav, int n_samples_max, int n_frames, const int* __restrict__ lengths,
+                                                     const float* __restrict__ filt_t, int n_mels, float* __restrict__ out, float* __restrict__ scratch) {
   __shared__ float s_cos[NFFT];
   __shared__ float s_sin[NFFT];
   __shared__ float s_x[FR][NFFT];      // windowed frames
@@ -41,7 +41,11 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
   __shared__ float s_red[8];
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * FR;
-  const float* w = wav + static_cast<int64_t>(b) * n_samples;
+  const float* w = wav + static_cast<int64_t>(b) * n_samples_max;
+  // variable-length batches (dynamic-frame recipes): utterance b has lengths[b] real samples; frames beyond its own
+  // n_valid/160 are zero padding of the MEL (the reference pads mel, not audio: speech_dataset_large.py:196-199)
+  const int n_samples = lengths != nullptr ? min(lengths[b], n_samples_max) : n_samples_max;
+  const int n_valid_frames = n_samples / HOP;
 
   for (int n = threadIdx.x; n < NFFT; n += blockDim.x) {
     float sn, cs;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
     const int f = i / NFFT, n = i - f * NFFT;
     const int t = f0 + f;
     float v = 0.0f;
-    if (t < n_frames) {
+    if (t < n_valid_frames) {
       int j = t * HOP + n - NFFT / 2;  // index into the un-padded waveform
       if (j < 0) j = -j;               // reflect padding (torch.stft center=True, pad_mode="reflect")
       if (j >= n_samples) j = 2 * (n_samples - 1) - j;
@@ -94,6 +98,10 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
     const int f = i / n_mels, m = i - f * n_mels;
     const int t = f0 + f;
     if (t >= n_frames) continue;
+    if (t >= n_valid_frames) {
+      out[(static_cast<int64_t>(b) * n_frames + t) * n_mels + m] = 0.0f;
+      continue;
+    }
     float acc = 0.0f;
     for (int k = 0; k < NBIN; ++k) acc = fmaf(filt_t[k * n_mels + m], s_pow[f][k], acc);
     const float lg = log10f(fmaxf(acc, 1e-10f));
@@ -110,19 +118,21 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
   }
 }
 
-__global__ void logmel_norm_kernel(float* __restrict__ out, const float* __restrict__ scratch, int64_t per_utt) {
+__global__ void logmel_norm_kernel(float* __restrict__ out, const float* __restrict__ scratch, int64_t per_utt, const int* __restrict__ lengths,
+                                   int n_samples_max, int n_mels) {
   const int b = blockIdx.y;
   const float gmax = key_float(reinterpret_cast<const int*>(scratch)[b]);
   float* o = out + static_cast<int64_t>(b) * per_utt;
+  const int64_t valid = lengths != nullptr ? static_cast<int64_t>(min(lengths[b], n_samples_max) / HOP) * n_mels : per_utt;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (; i < per_utt; i += stride) o[i] = (fmaxf(o[i], gmax - 8.0f) + 4.0f) / 4.0f;
+  for (; i < valid; i += stride) o[i] = (fmaxf(o[i], gmax - 8.0f) + 4.0f) / 4.0f;
 }
 
 }  // namespace slam
 
-extern "C" int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, const float* filters_t, int32_t n_mels, float* out,
-                           float* scratch_max, void* stream) {
+extern "C" int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, const int32_t* lengths, const float* filters_t, int32_t n_mels,
+                           float* out, float* scratch_max, void* stream) {
   using namespace slam;
   SLAM_CHECK_ARG(batch > 0 && n_samples > NFFT && n_mels > 0 && n_mels <= 256, "logmel: bad shape batch=%d n_samples=%d n_mels=%d", batch,
                  n_samples, n_mels);
@@ -131,11 +141,11 @@ extern "C" int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, c
   logmel_init_kernel<<<static_cast<unsigned>(ceil_div(batch, 128)), 128, 0, st>>>(scratch_max, batch);
   SLAM_LAUNCH_CHECK("slam_logmel.init");
   dim3 grid(static_cast<unsigned>(ceil_div(n_frames, FR)), batch);
-  logmel_kernel<<<grid, 256, 0, st>>>(wav, n_samples, n_frames, filters_t, n_mels, out, scratch_max);
+  logmel_kernel<<<grid, 256, 0, st>>>(wav, n_samples, n_frames, lengths, filters_t, n_mels, out, scratch_max);
   SLAM_LAUNCH_CHECK("slam_logmel");
   const int64_t per_utt = static_cast<int64_t>(n_frames) * n_mels;
   dim3 g2(static_cast<unsigned>(ceil_div(per_utt, 256 * 4) > 296 ? 296 : ceil_div(per_utt, 256 * 4)), batch);
-  logmel_norm_kernel<<<g2, 256, 0, st>>>(out, scratch_max, per_utt);
+  logmel_norm_kernel<<<g2, 256, 0, st>>>(out, scratch_max, per_utt, lengths, n_samples, n_mels);
   SLAM_LAUNCH_CHECK("slam_logmel.norm");
   return 0;
 }

@@ -162,6 +162,84 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const bf16* __restrict_
   }
 }
 
+// Tensor-core variant (mma.sync m16n8k16): C[P,Q] += scale * A[m0:m1, :P]^T B[m0:m1, q0:q0+256].  One CTA = 256 output
+// columns x an M-chunk; A^T and B fragments come from cp.async-staged shared tiles through ldmatrix.trans.
+__device__ __forceinline__ void wg_cp16(void* dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+template <int PT>  // 16-row tiles of P
+__global__ void __launch_bounds__(128) wgrad_thin_mma_kernel(const bf16* __restrict__ a, long long lda, int pdim, const bf16* __restrict__ bm,
+                                                             long long ldb, int qdim, int m, int m_chunk, float scale, float* __restrict__ c,
+                                                             long long ldc) {
+  constexpr int MC = 64, QT = 256, APITCH = PT * 16 + 8, BPITCH = QT + 8;
+  __shared__ __align__(16) bf16 sA[MC * APITCH];
+  __shared__ __align__(16) bf16 sB[MC * BPITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int m_begin = blockIdx.y * m_chunk;
+  const int m_end = min(m, m_begin + m_chunk);
+  float acc[PT][8][4];
+#pragma unroll
+  for (int i = 0; i < PT; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
+
+  for (int mb = m_begin; mb < m_end; mb += MC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < MC * (PT * 2); i += 128) {          // A chunk: MC rows x (PT*16) cols, 16-byte pieces
+      const int r = i / (PT * 2), pc = (i % (PT * 2)) * 8;
+      const bool ok = (mb + r) < m_end && pc < pdim;
+      wg_cp16(sA + r * APITCH + pc, a + (ok ? static_cast<long long>(mb + r) * lda + pc : 0), ok ? 16 : 0);
+    }
+    for (int i = threadIdx.x; i < MC * (QT / 8); i += 128) {          // B chunk: MC rows x 256 cols
+      const int r = i / (QT / 8), qc = (i % (QT / 8)) * 8;
+      const bool ok = (mb + r) < m_end && (q0 + qc) < qdim;
+      wg_cp16(sB + r * BPITCH + qc, bm + (ok ? static_cast<long long>(mb + r) * ldb + q0 + qc : 0), ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < MC / 16; ++ks) {
+      uint32_t af[PT][4];
+#pragma unroll
+      for (int pt = 0; pt < PT; ++pt) {
+        const bf16* ap = sA + (ks * 16 + (lane & 7) + (lane >> 4) * 8) * APITCH + pt * 16 + ((lane >> 3) & 1) * 8;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(af[pt][0]), "=r"(af[pt][1]), "=r"(af[pt][2]), "=r"(af[pt][3])
+                     : "r"(smem_u32(ap)));
+      }
+#pragma unroll
+      for (int nb2 = 0; nb2 < 4; ++nb2) {
+        uint32_t bf[4];
+        const bf16* bp = sB + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * BPITCH + warp * 64 + nb2 * 16 + (lane >> 4) * 8;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bf[0]), "=r"(bf[1]), "=r"(bf[2]), "=r"(bf[3])
+                     : "r"(smem_u32(bp)));
+#pragma unroll
+        for (int pt = 0; pt < PT; ++pt) {
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[pt][2 * nb2][0]), "+f"(acc[pt][2 * nb2][1]), "+f"(acc[pt][2 * nb2][2]), "+f"(acc[pt][2 * nb2][3])
+                       : "r"(af[pt][0]), "r"(af[pt][1]), "r"(af[pt][2]), "r"(af[pt][3]), "r"(bf[0]), "r"(bf[1]));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[pt][2 * nb2 + 1][0]), "+f"(acc[pt][2 * nb2 + 1][1]), "+f"(acc[pt][2 * nb2 + 1][2]), "+f"(acc[pt][2 * nb2 + 1][3])
+                       : "r"(af[pt][0]), "r"(af[pt][1]), "r"(af[pt][2]), "r"(af[pt][3]), "r"(bf[2]), "r"(bf[3]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int pt = 0; pt < PT; ++pt)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int pr = pt * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+        const int qc = q0 + warp * 64 + nb * 8 + 2 * (lane & 3) + (e & 1);
+        if (pr < pdim && qc < qdim) atomicAdd(c + static_cast<long long>(pr) * ldc + qc, acc[pt][nb][e] * scale);
+      }
+}
+
 __global__ void zero2d_kernel(float* c, long long ldc, int rows, int cols) {
   const long long total = static_cast<long long>(rows) * cols;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -215,6 +293,23 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
   if (zb > 1184) zb = 1184;
   zero2d_kernel<<<static_cast<unsigned>(zb), 256, 0, st>>>(c, ldc, p, q);
   SLAM_LAUNCH_CHECK("slam_wgrad_thin.zero");
+  const bf16* ap = reinterpret_cast<const bf16*>(a);
+  const bf16* bp = reinterpret_cast<const bf16*>(b);
+  const bool aligned = p % 8 == 0 && q % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+  if (aligned) {
+    // tensor-core path: 256 output columns x 128 rows of M per CTA
+    const int m_chunk = 128;
+    dim3 grid(static_cast<unsigned>(ceil_div(q, 256)), static_cast<unsigned>(ceil_div(m, m_chunk)));
+    if (p <= 16)
+      wgrad_thin_mma_kernel<1><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    else if (p <= 32)
+      wgrad_thin_mma_kernel<2><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    else
+      wgrad_thin_mma_kernel<4><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    SLAM_LAUNCH_CHECK("slam_wgrad_thin.mma");
+    return 0;
+  }
   const int qblocks = static_cast<int>(ceil_div(q, 64));
   // ~128 rows of M per block: many short blocks (atomics merge the partial sums) instead of few long latency-bound ones
   int m_chunk = 128;
@@ -225,8 +320,6 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
     ysplit = static_cast<int>(ceil_div(m, m_chunk));
   }
   dim3 grid(qblocks, ysplit);
-  const bf16* ap = reinterpret_cast<const bf16*>(a);
-  const bf16* bp = reinterpret_cast<const bf16*>(b);
   if (p <= 16)
     wgrad_thin_kernel<16><<<grid, 256, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
   else if (p <= 32)

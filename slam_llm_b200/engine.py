@@ -558,9 +558,11 @@ class SlamStepB200:
         return loaded
 
     # ------------------------------------------------------------------ front end
-    def log_mel(self, pcm: torch.Tensor) -> torch.Tensor:
-        """pcm f32 [B, n_samples] on device -> [B, n_samples//160, n_mels]."""
-        return ops.logmel(pcm.contiguous(), self.filters_t)
+    def log_mel(self, pcm: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pcm f32 [B, n_samples] on device (+ optional i32 [B] real lengths) -> [B, n_samples//160, n_mels]."""
+        if lengths is not None:
+            lengths = lengths.to(self.device, torch.int32).contiguous()
+        return ops.logmel(pcm.contiguous(), self.filters_t, lengths=lengths)
 
     # ------------------------------------------------------------------ forward
     @staticmethod
@@ -588,7 +590,7 @@ class SlamStepB200:
         mod_mask = batch["modality_mask"].to(dev).to(torch.uint8).contiguous()
         mel = batch.get("audio_mel")
         if mel is None:
-            mel = self.log_mel(batch["audio_pcm"].to(dev, F32))
+            mel = self.log_mel(batch["audio_pcm"].to(dev, F32), batch.get("audio_pcm_lengths"))
         else:
             mel = mel.to(dev, F32)
         B, S = ids.shape

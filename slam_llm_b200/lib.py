@@ -61,7 +61,7 @@ _SIGS = {
     "slam_launch_count": [],
     "slam_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "slam_wgrad_thin": [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp],
-    "slam_logmel": [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp],
+    "slam_logmel": [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "slam_conv_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "slam_add_pos": [_vp, _vp, _i32, _i32, _i32, _vp],
     "slam_layernorm": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],

@@ -116,8 +116,9 @@ def wgrad_thin(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scale: float
 
 
 # ------------------------------------------------------------------------------------------- front end
-def logmel(wav: torch.Tensor, filters_t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """wav f32 [B, n_samples] -> log-mel f32 [B, n_samples//160, n_mels] (whisper.log_mel_spectrogram, time-major)."""
+def logmel(wav: torch.Tensor, filters_t: torch.Tensor, out: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wav f32 [B, n_samples] -> log-mel f32 [B, n_samples//160, n_mels] (whisper.log_mel_spectrogram, time-major).
+    lengths (i32 [B], optional): real sample counts of a zero-padded variable-length batch."""
     _req(wav, F32, "logmel.wav"); _req(filters_t, F32, "logmel.filters_t")
     assert wav.dim() == 2 and wav.is_contiguous() and filters_t.is_contiguous() and filters_t.shape[0] == 201
     B, n = wav.shape
@@ -125,7 +126,9 @@ def logmel(wav: torch.Tensor, filters_t: torch.Tensor, out: Optional[torch.Tenso
     if out is None:
         out = torch.empty((B, n // 160, n_mels), device=wav.device, dtype=F32)
     scratch = torch.empty((B,), device=wav.device, dtype=F32)
-    _l.check(_l.load().slam_logmel(wav.data_ptr(), B, n, filters_t.data_ptr(), n_mels, out.data_ptr(), scratch.data_ptr(), _stream()),
+    if lengths is not None:
+        assert lengths.dtype == torch.int32 and lengths.is_cuda and lengths.numel() == B and lengths.is_contiguous()
+    _l.check(_l.load().slam_logmel(wav.data_ptr(), B, n, _p(lengths), filters_t.data_ptr(), n_mels, out.data_ptr(), scratch.data_ptr(), _stream()),
              "slam_logmel")
     return out
 

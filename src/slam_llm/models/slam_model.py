@@ -309,7 +309,7 @@ class slam_model(nn.Module):
             batch["audio_mel"] = audio_mel
         else:
             batch["audio_pcm"] = audio_pcm
-        for k in ("_rows", "_targets"):
+        for k in ("_rows", "_targets", "audio_pcm_lengths"):
             if kwargs.get(k, None) is not None:
                 batch[k] = kwargs[k]
         if kwargs.get("inference_mode", False):
@@ -328,7 +328,7 @@ class slam_model(nn.Module):
         from slam_llm_b200 import ops
         dev = self.b200.device
         mel = batch.get("audio_mel")
-        mel = self.b200.log_mel(batch["audio_pcm"].to(dev, torch.float32)) if mel is None else mel.to(dev, torch.float32)
+        mel = self.b200.log_mel(batch["audio_pcm"].to(dev, torch.float32), batch.get("audio_pcm_lengths")) if mel is None else mel.to(dev, torch.float32)
         aud = self.b200.projector.forward(self.b200.encoder.forward(mel), save=False)
         return ops.embed_merge(batch["input_ids"].to(dev).contiguous(), batch["modality_mask"].to(dev).to(torch.uint8).contiguous(), aud,
                                self.b200.llm.embed)

@@ -290,3 +290,42 @@ def test_reference_recipe_files_import_unchanged_against_the_mirror(monkeypatch)
     assert issubclass(model_mod.slam_model_asr, sm.slam_model) and callable(model_mod.model_factory)
     from slam_llm.pipeline.finetune import main
     assert ft.train is main
+
+
+# ------------------------------------------------------------------------------------------------- dynamic-frame batching (config 3)
+def test_dynamic_frame_dataset_window_rule_and_right_padding(tmp_path):
+    from slam_llm.datasets.speech_dataset_large import get_speech_dataset, window_class
+    data_dir = tmp_path / "scp"
+    data_dir.mkdir()
+    secs = [1.0, 3.2, 0.5, 2.0, 31.0, 1.5, 0.9]                       # the 31 s item exceeds max_audio_length and is skipped
+    rows = []
+    for i, sec in enumerate(secs):
+        _write_wav(data_dir / f"{i}.wav", sec, 100 + i)
+        rows.append({"key": f"k{i}", "task": "ASR", "target": "word " * (1 + i % 3), "path": str(data_dir / f"{i}.wav")})
+    (data_dir / "multitask.jsonl").write_text("\n".join(json.dumps(r) for r in rows))
+    (tmp_path / "prompt.jsonl").write_text(json.dumps({"task": "ASR", "prompt": "Transcribe speech to text."}))
+    cfg = DictConfig({"append_info_tasks": [], "multitask_prompt_path": str(tmp_path / "prompt.jsonl"), "train_scp_file_path": str(data_dir),
+                      "dev_scp_file_path": str(data_dir), "test_scp_file_path": str(data_dir), "input_type": "mel", "mel_size": 80,
+                      "prompt_style": "USER: {}\n ASSISTANT:", "train_max_frame_length": 260, "eval_max_frame_length": 10000, "max_audio_length": 30})
+    ds = get_speech_dataset(cfg, FakeTokenizer(), "train")
+    batches = list(ds)
+    n_items = sum(len(b) for b in batches)
+    assert n_items == len(secs) - 1
+    for b in batches:                                                  # the reference rule: B * longest <= budget (single items always pass)
+        assert len(b) == 1 or len(b) * max(len(x["input_ids"]) for x in b) <= 260
+    assert window_class({"input_ids": [0] * 100}, [], 10) is True      # empty buffer always "flushes" (then starts a new one)
+    assert window_class({"input_ids": [0] * 100}, [{"input_ids": [0] * 120}], 240) is False
+    assert window_class({"input_ids": [0] * 100}, [{"input_ids": [0] * 121}], 240) is True
+    big = max(batches, key=len)
+    out = ds.collator(big)
+    B, S = out["input_ids"].shape
+    assert out["audio_mel"] is None and out["audio_pcm"].shape[0] == B and out["audio_pcm"].shape[1] % 320 == 0
+    assert out["audio_pcm_lengths"].dtype == torch.int32 and out["audio_pcm_lengths"].tolist() == [x["audio_pcm"].shape[0] for x in big]
+    for i, x in enumerate(big):                                        # RIGHT padding only; audio tokens first
+        n = len(x["input_ids"])
+        assert out["attention_mask"][i, :n].all() and not out["attention_mask"][i, n:].any()
+        assert out["modality_mask"][i, : x["audio_length"]].all() and out["modality_mask"][i].sum().item() == x["audio_length"]
+        assert x["audio_length"] == ((x["audio_pcm"].shape[0] // 160 + 1) // 2) // 5
+        assert (out["labels"][i, n:] == -100).all()
+    eval_batches = list(get_speech_dataset(cfg, FakeTokenizer(), "val"))
+    assert len(eval_batches) == 1 and len(eval_batches[0]) == len(secs) - 1

@@ -116,6 +116,12 @@ def test_wgrad_thin(ops):
     ops.wgrad_thin(a, b, out, scale=2.0)
     ref = 2.0 * a.float().t() @ b.float()
     assert rel_err(out, ref) < 1e-4
+    for (Mx, Px, Qx, ld) in ((1601, 8, 1024, 64), (333, 64, 6144, 64), (1600, 32, 520, 32), (70, 16, 4096, 16)):   # tensor-core path
+        af = rnd(Mx, ld, seed=50)
+        bx = rnd(Mx, Qx + 8, seed=51)[:, :Qx]
+        o = torch.empty(Px, Qx, device=dev(), dtype=F32)
+        ops.wgrad_thin(af[:, :Px], bx, o, scale=0.5)
+        assert rel_err(o, 0.5 * af[:, :Px].float().t() @ bx.float()) < 1e-4, (Mx, Px, Qx)
     out2 = torch.empty(40, 300, device=dev(), dtype=F32)
     a2, b2 = rnd(77, 40, seed=16), rnd(77, 300, seed=17)
     ops.wgrad_thin(a2, b2, out2)
@@ -148,6 +154,22 @@ def test_logmel(ops, n_mels, n_samples):
     assert out.shape == ref.shape
     # fp32 direct DFT vs fp64 FFT reference, after log compression: absolute tolerance on the (x+4)/4 scale
     assert (out - ref).abs().max().item() < 2e-3, (out - ref).abs().max().item()
+
+
+def test_logmel_variable_lengths(ops):
+    """Dynamic-frame batches: each utterance is transformed on ITS OWN length and the mel (not the audio) is zero padded."""
+    n_mels, n_max = 80, 40000
+    lens = [40000, 23456, 16000]
+    wav = rnd(3, n_max, scale=0.1, dtype=F32, seed=77)
+    for i, n in enumerate(lens):
+        wav[i, n:] = 0.0
+    filt = _mel_filters(n_mels)
+    out = ops.logmel(wav, filt.t().contiguous(), lengths=torch.tensor(lens, dtype=torch.int32, device=dev()))
+    assert out.shape == (3, n_max // 160, n_mels)
+    for i, n in enumerate(lens):
+        ref = _ref_logmel(wav[i:i + 1, :n].double(), filt.double()).float()[0]      # [n//160, n_mels]
+        assert (out[i, : n // 160] - ref).abs().max().item() < 2e-3
+        assert out[i, n // 160:].abs().max().item() == 0.0
 
 
 def test_conv_stem_im2col(ops):
