@@ -112,6 +112,8 @@ typedef struct slam_attn_args {
   void* dv; int64_t lddv;
   float* delta;                  /* f32 [B,Hq,Sq] scratch */
   float* dq_accum;               /* f32 scratch [B,Sq,Hq,dh]: dQ partial sums (zeroed by the call) */
+  void* dkv_part;                /* optional bf16 scratch [2,B,Sk,Hq,dh] (GQA only): per-Q-head dK/dV partials, summed over each
+                                    KV group by a follow-up kernel -> Hq/Hkv times more CTAs; NULL = loop over the group in one CTA */
 } slam_attn_args;
 int slam_attn_fwd(const slam_attn_args* a, void* stream);
 int slam_attn_bwd(const slam_attn_args* a, void* stream);

@@ -50,6 +50,7 @@ struct AttnP {
   bf16* dv; long long lddv;
   float* delta;
   float* dq_accum;
+  bf16* dkv_part;   // optional [2][B][Sk][Hq][dh]: per-q-head dK/dV partials (GQA): 4x more CTAs, group-summed afterwards
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -305,9 +306,15 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
   float* sLseB = reinterpret_cast<float*>(sdS + BN * SPITCH);  // 2 stages of lse (log2 domain) ...
   float* sDeltaB = sLseB + 2 * BQ;                             // ... and delta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hk = blockIdx.y, b = blockIdx.z;
+  const int b = blockIdx.z;
   const int k0 = blockIdx.x * BN;
-  const int group = p.hq / p.hkv;
+  // split_heads: one CTA per (key block, Q head) writing per-head dK/dV partials (more parallelism, shorter critical path);
+  // otherwise one CTA per (key block, KV head) looping over the heads of its group with dK/dV kept in registers
+  const bool split_heads = p.dkv_part != nullptr;
+  const int group_all = p.hq / p.hkv;
+  const int hk = split_heads ? static_cast<int>(blockIdx.y) / group_all : static_cast<int>(blockIdx.y);
+  const int h_first = split_heads ? static_cast<int>(blockIdx.y) : hk * group_all;
+  const int group = split_heads ? 1 : group_all;
   const float scale_log2 = p.scale * kLog2e;
 
   load_tile<DH, BN, 128>(sK, p.k + (static_cast<long long>(b) * p.sk + k0) * p.ldk + hk * DH, p.ldk, min(BN, p.sk - k0));
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
 
   // stage j of the (head-in-group, query-block) sequence -> shared stage j & 1 (cp.async: overlaps the MMAs of stage j-1)
   auto prefetch = [&](int j) {
-    const int h = hk * group + j / nq;
+    const int h = h_first + j / nq;
     const int q0 = q_start + (j % nq) * BQ;
     const int vq = min(BQ, p.sq - q0);
     const int st = j & 1;
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
 
   for (int j = 0; j < n_iter; ++j) {
     {
-      const int h = hk * group + j / nq;
+      const int h = h_first + j / nq;
       const int q0 = q_start + (j % nq) * BQ;
       cp_async_wait<0>();
       __syncthreads();                      // stage j landed; everyone is done with stage j-1 (and with sdS)
@@ -479,12 +486,45 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
     if (key < p.sk) {
       bf16* dkr = p.dk + (static_cast<long long>(b) * p.sk + key) * p.lddk + hk * DH;
       bf16* dvr = p.dv + (static_cast<long long>(b) * p.sk + key) * p.lddv + hk * DH;
+      if (split_heads) {
+        const long long part = static_cast<long long>(p.batch) * p.sk * p.hq * DH;
+        dkr = p.dkv_part + ((static_cast<long long>(b) * p.sk + key) * p.hq + h_first) * DH;
+        dvr = dkr + part;
+      }
 #pragma unroll
       for (int i = 0; i < DH / 8; ++i) {
         *reinterpret_cast<uint32_t*>(dkr + i * 8 + 2 * (lane & 3)) = pack_bf16x2(dk[i][2 * r], dk[i][2 * r + 1]);
         *reinterpret_cast<uint32_t*>(dvr + i * 8 + 2 * (lane & 3)) = pack_bf16x2(dv[i][2 * r], dv[i][2 * r + 1]);
       }
     }
+  }
+}
+
+// dK/dV partials [2][rows][Hq][dh] (bf16) -> sum over the G heads of each KV group -> dk/dv [rows][Hkv][dh] with row strides
+__global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __restrict__ dk, long long lddk, bf16* __restrict__ dv, long long lddv,
+                                      long long rows, int hq, int hkv, int dh) {
+  const int g = hq / hkv;
+  const int vec_per_row = hkv * dh / 8;
+  const long long total = 2 * rows * vec_per_row;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const int which = static_cast<int>(i / (rows * vec_per_row));
+    const long long rem = i % (rows * vec_per_row);
+    const long long r = rem / vec_per_row;
+    const int c = static_cast<int>(rem % vec_per_row) * 8;      // column inside [hkv*dh]
+    const int hk = c / dh, d0 = c % dh;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bf16* src = part + (static_cast<long long>(which) * rows + r) * hq * dh + static_cast<long long>(hk) * g * dh + d0;
+    for (int j = 0; j < g; ++j) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(j) * dh);
+      const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y; acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    bf16* dst = (which == 0 ? dk + r * lddk : dv + r * lddv) + c;
+    *reinterpret_cast<uint4*>(dst) = o;
   }
 }
 
@@ -526,6 +566,7 @@ static int fill_params(const slam_attn_args* a, AttnP& p, bool bwd) {
   p.dv = reinterpret_cast<bf16*>(a->dv); p.lddv = a->lddv;
   p.delta = a->delta;
   p.dq_accum = a->dq_accum;
+  p.dkv_part = (bwd && a->hq != a->hkv) ? reinterpret_cast<bf16*>(a->dkv_part) : nullptr;
   if (bwd) {
     SLAM_CHECK_ARG(a->lse && a->delta && a->dq_accum && a->dout && a->dq && a->dk && a->dv, "attn_bwd: missing buffers");
     SLAM_CHECK_ARG(a->lddo % 8 == 0 && a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0, "attn_bwd: row strides must be multiples of 8");
@@ -554,7 +595,7 @@ static int launch_bwd(const AttnP& p, cudaStream_t st) {
     cudaFuncSetAttribute(attn_bwd_kernel<DH, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     set = true;
   }
-  dim3 grid(static_cast<unsigned>(ceil_div(p.sk, 64)), p.hkv, p.batch);
+  dim3 grid(static_cast<unsigned>(ceil_div(p.sk, 64)), p.dkv_part != nullptr ? p.hq : p.hkv, p.batch);
   attn_bwd_kernel<DH, BQ><<<grid, 128, SMEM, st>>>(p);
   SLAM_LAUNCH_CHECK("slam_attn_bwd");
   return 0;
@@ -595,6 +636,13 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
   SLAM_LAUNCH_CHECK("slam_attn_bwd.delta");
   rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
   if (rc != 0) return rc;
+  if (p.dkv_part != nullptr) {
+    const long long krows = static_cast<long long>(p.batch) * p.sk;
+    long long gb = ceil_div(2 * krows * (p.hkv * a->dh / 8), 256);
+    if (gb > num_sms() * 16) gb = num_sms() * 16;
+    attn_group_sum_kernel<<<static_cast<unsigned>(gb), 256, 0, st>>>(p.dkv_part, p.dk, p.lddk, p.dv, p.lddv, krows, p.hq, p.hkv, a->dh);
+    SLAM_LAUNCH_CHECK("slam_attn_bwd.group_sum");
+  }
   SLAM_CHECK_ARG(p.lddq >= width || p.hq * a->dh <= p.lddq, "attn_bwd: lddq too small");
   const long long nvec = rows * (width / 4);
   long long blocks = ceil_div(nvec, 256);

@@ -51,6 +51,7 @@ class AttnArgs(C.Structure):
         ("dv", _vp), ("lddv", _i64),
         ("delta", _vp),
         ("dq_accum", _vp),
+        ("dkv_part", _vp),
     ]
 
 

@@ -217,6 +217,8 @@ def attn_bwd(q, k, v, out, lse, dout, *, causal: bool, scale: float, key_mask=No
     delta = torch.empty((B, Hq, Sq), device=q.device, dtype=F32)
     dq_accum = torch.empty((B, Sq, Hq, dh), device=q.device, dtype=F32)
     a.delta, a.dq_accum = delta.data_ptr(), dq_accum.data_ptr()
+    dkv_part = torch.empty((2, B, Sk, Hq, dh), device=q.device, dtype=BF16) if Hq != Hkv else None   # GQA: split CTAs per Q head
+    a.dkv_part = _p(dkv_part)
     _l.check(_l.load().slam_attn_bwd(C.byref(a), _stream()), "slam_attn_bwd")
     return dq, dk, dv
 

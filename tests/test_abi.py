@@ -35,13 +35,13 @@ def test_struct_layout_matches_c_compiler(lib, tmp_path):
                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(slam_gemm_args), offsetof(slam_gemm_args, out), offsetof(slam_gemm_args, alpha), '
                    'offsetof(slam_gemm_args, block_n), offsetof(slam_gemm_args, k2));\n'
                    'printf("%zu %zu %zu %zu\\n", sizeof(slam_attn_args), offsetof(slam_attn_args, scale), offsetof(slam_attn_args, dout), '
-                   'offsetof(slam_attn_args, dq_accum));\nreturn 0;}\n')
+                   'offsetof(slam_attn_args, dkv_part));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
     g, a = lib.GemmArgs, lib.AttnArgs
     assert [int(x) for x in out[:5]] == [ctypes.sizeof(g), g.out.offset, g.alpha.offset, g.block_n.offset, g.k2.offset]
-    assert [int(x) for x in out[5:]] == [ctypes.sizeof(a), a.scale.offset, a.dout.offset, a.dq_accum.offset]
+    assert [int(x) for x in out[5:]] == [ctypes.sizeof(a), a.scale.offset, a.dout.offset, a.dkv_part.offset]
 
 
 def test_header_is_plain_c_and_cites_reference(lib):

@@ -169,7 +169,8 @@ def test_logmel_variable_lengths(ops):
     for i, n in enumerate(lens):
         ref = _ref_logmel(wav[i:i + 1, :n].double(), filt.double()).float()[0]      # [n//160, n_mels]
         assert (out[i, : n // 160] - ref).abs().max().item() < 2e-3
-        assert out[i, n // 160:].abs().max().item() == 0.0
+        if n // 160 < n_max // 160:
+            assert out[i, n // 160:].abs().max().item() == 0.0
 
 
 def test_conv_stem_im2col(ops):
