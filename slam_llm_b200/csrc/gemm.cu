@@ -26,7 +26,7 @@ namespace slam {
 
 constexpr int GEMM_BK = 64;
 #ifndef SLAM_GEMM_PREFETCH
-#define SLAM_GEMM_PREFETCH 8   // L2 prefetch distance of the weight operand, in k-blocks (0 = off)
+#define SLAM_GEMM_PREFETCH 0   // L2 prefetch distance of the weight operand in k-blocks; measured on B200: 4/8/16 are ~10 % SLOWER than 0 (profiles/r01_exp_prefetch.log)
 #endif
 constexpr int GEMM_THREADS = 256;
 
