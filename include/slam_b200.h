@@ -56,6 +56,9 @@ typedef struct slam_gemm_args {
   int32_t m, n;
   int32_t block_n;                /* tile override: 0 = auto; 64/128/192/256 = BLOCK_N with 128-row tiles;
                                      BLOCK_M*1000+BLOCK_N (e.g. 256256) = explicit 256-row tile */
+  int32_t split_k;                /* <= 1: off.  > 1: K is cut into that many slices processed by different CTAs and merged with
+                                     fp32 atomics into `out`, which must be f32 and ZERO-INITIALISED by the caller; no bias /
+                                     activation / residual (thin LoRA products, lm_head dgrad: few output tiles, long K) */
 } slam_gemm_args;
 int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
 
@@ -145,6 +148,13 @@ int slam_rope(void* x_bf16, int64_t ld, int32_t rows, int32_t seq_len, int32_t n
 int slam_swiglu_fwd(const void* gu_bf16, void* h_bf16, int32_t rows, int32_t f, void* stream);
 int slam_swiglu_bwd(const void* gu_bf16, const void* dh_bf16, void* dgu_bf16, int32_t rows, int32_t f,
                     void* stream);
+
+/* a6  LoRA-branch dropout (peft lora.Linear.forward: lora_B(lora_A(dropout(x))) — train_config.peft_config.lora_dropout).
+ *   y = x * keep / (1-p) with keep(i) = hash(seed, i) >= p; the backward regenerates the same mask from (seed, i):
+ *   out = base + lora * keep / (1-p)   (dX = dY W  +  mask o ((dY sB) A)).  n % 8 == 0; bf16. */
+int slam_dropout(const void* x_bf16, void* y_bf16, int64_t n, float p, uint64_t seed, void* stream);
+int slam_dropout_bwd_add(const void* base_bf16, const void* lora_bf16, void* out_bf16, int64_t n, float p, uint64_t seed,
+                         void* stream);
 
 /* a7  token cross-entropy + accuracy on fp32 logits rows (HF ForCausalLMLoss + utils/metric.py:3-20).
  *   logits f32 [R,V] (rows already shifted/selected by the host), targets i64 [R] (-100 = ignore).

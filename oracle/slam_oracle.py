@@ -360,17 +360,21 @@ def rotate_half(x: torch.Tensor) -> torch.Tensor:
     return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
 
 
-def lora_linear(x: torch.Tensor, weight: torch.Tensor, lw: Dict[str, torch.Tensor], prefix: str, lora: Optional[LoraCfg]) -> torch.Tensor:
-    """peft 0.6 lora.Linear.forward with dropout = 0: F.linear(x, W) + B(A(x)) * alpha/r."""
+def lora_linear(x: torch.Tensor, weight: torch.Tensor, lw: Dict[str, torch.Tensor], prefix: str, lora: Optional[LoraCfg],
+                masks: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """peft 0.6 lora.Linear.forward: F.linear(x, W) + B(A(dropout(x))) * alpha/r.  Dropout is deterministic here: `masks`
+    (prefix -> keep/(1-p) tensor shaped like x) stands in for nn.Dropout's random mask; None = dropout 0."""
     y = F.linear(x, weight)
     a_key = prefix + "lora_A.default.weight"
     if lora is not None and a_key in lw:
-        y = y + F.linear(F.linear(x, lw[a_key]), lw[prefix + "lora_B.default.weight"]) * lora.scaling
+        xd = x if masks is None or prefix not in masks else x * masks[prefix].view_as(x)
+        y = y + F.linear(F.linear(xd, lw[a_key]), lw[prefix + "lora_B.default.weight"]) * lora.scaling
     return y
 
 
 def llama_forward(w: Dict[str, torch.Tensor], lw: Dict[str, torch.Tensor], cfg: LlmCfg, lora: Optional[LoraCfg],
-                  inputs_embeds: torch.Tensor, attention_mask: torch.Tensor, return_hidden: bool = False):
+                  inputs_embeds: torch.Tensor, attention_mask: torch.Tensor, return_hidden: bool = False,
+                  lora_masks: Optional[Dict[str, torch.Tensor]] = None):
     """inputs_embeds [B,S,D], attention_mask bool/int [B,S] (1 = real token) -> logits f32 [B,S,V]."""
     B, S, D = inputs_embeds.shape
     H, Hkv, dh = cfg.heads, cfg.kv_heads, cfg.dh
@@ -384,9 +388,9 @@ def llama_forward(w: Dict[str, torch.Tensor], lw: Dict[str, torch.Tensor], cfg: 
     for i in range(cfg.layers):
         p = f"model.layers.{i}."
         h = rms_norm(x, w[p + "input_layernorm.weight"], cfg.eps)
-        q = lora_linear(h, w[p + "self_attn.q_proj.weight"], lw, p + "self_attn.q_proj.", lora)
-        k = lora_linear(h, w[p + "self_attn.k_proj.weight"], lw, p + "self_attn.k_proj.", lora)
-        v = lora_linear(h, w[p + "self_attn.v_proj.weight"], lw, p + "self_attn.v_proj.", lora)
+        q = lora_linear(h, w[p + "self_attn.q_proj.weight"], lw, p + "self_attn.q_proj.", lora, lora_masks)
+        k = lora_linear(h, w[p + "self_attn.k_proj.weight"], lw, p + "self_attn.k_proj.", lora, lora_masks)
+        v = lora_linear(h, w[p + "self_attn.v_proj.weight"], lw, p + "self_attn.v_proj.", lora, lora_masks)
         q = q.view(B, S, H, dh).transpose(1, 2)
         k = k.view(B, S, Hkv, dh).transpose(1, 2)
         v = v.view(B, S, Hkv, dh).transpose(1, 2)
@@ -397,11 +401,11 @@ def llama_forward(w: Dict[str, torch.Tensor], lw: Dict[str, torch.Tensor], cfg: 
         att = q @ k.transpose(2, 3) / math.sqrt(dh) + add_mask
         att = torch.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
         o = (att @ v).transpose(1, 2).reshape(B, S, D)
-        x = x + lora_linear(o, w[p + "self_attn.o_proj.weight"], lw, p + "self_attn.o_proj.", lora)
+        x = x + lora_linear(o, w[p + "self_attn.o_proj.weight"], lw, p + "self_attn.o_proj.", lora, lora_masks)
         h = rms_norm(x, w[p + "post_attention_layernorm.weight"], cfg.eps)
-        g = lora_linear(h, w[p + "mlp.gate_proj.weight"], lw, p + "mlp.gate_proj.", lora)
-        u = lora_linear(h, w[p + "mlp.up_proj.weight"], lw, p + "mlp.up_proj.", lora)
-        x = x + lora_linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"], lw, p + "mlp.down_proj.", lora)
+        g = lora_linear(h, w[p + "mlp.gate_proj.weight"], lw, p + "mlp.gate_proj.", lora, lora_masks)
+        u = lora_linear(h, w[p + "mlp.up_proj.weight"], lw, p + "mlp.up_proj.", lora, lora_masks)
+        x = x + lora_linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"], lw, p + "mlp.down_proj.", lora, lora_masks)
         if return_hidden:
             hiddens.append(x)
     x = rms_norm(x, w["model.norm.weight"], cfg.eps)
@@ -463,7 +467,7 @@ class OracleModel:
         out.update({f"llm.base_model.model.{k}": v for k, v in self.lora_w.items()})
         return out
 
-    def forward(self, batch: Dict[str, torch.Tensor], return_all: bool = False):
+    def forward(self, batch: Dict[str, torch.Tensor], return_all: bool = False, lora_masks=None):
         """batch keys as produced by SpeechDatasetJsonl.collator (speech_dataset.py:216-291); audio either as
         `audio_mel` [B,T,n_mels] or raw `audio_pcm` [B,n] (log-mel computed here)."""
         mel = batch.get("audio_mel")
@@ -475,7 +479,7 @@ class OracleModel:
             enc = whisper_encoder(self.enc_w, self.enc_cfg, mel)
         aud = projector(self.proj_w, self.proj_cfg, enc)
         x = merge(self.llm_w["model.embed_tokens.weight"], batch["input_ids"], batch["modality_mask"].bool(), aud)
-        logits = llama_forward(self.llm_w, self.lora_w, self.llm_cfg, self.lora_cfg, x, batch["attention_mask"])
+        logits = llama_forward(self.llm_w, self.lora_w, self.llm_cfg, self.lora_cfg, x, batch["attention_mask"], lora_masks=lora_masks)
         labels = batch["labels"]
         loss = causal_lm_loss(logits, labels)
         preds = torch.argmax(logits, -1)
@@ -484,14 +488,14 @@ class OracleModel:
             return {"loss": loss, "acc": acc, "logits": logits, "encoder_out": enc, "audio_tokens": aud, "inputs_embeds": x, "mel": mel}
         return loss, acc
 
-    def step(self, batch, lr: float = 1e-4, weight_decay: float = 0.0, do_update: bool = True):
+    def step(self, batch, lr: float = 1e-4, weight_decay: float = 0.0, do_update: bool = True, lora_masks=None):
         """One optimizer step: forward, backward (grads only for projector + LoRA), AdamW.  Returns dict with
         loss, acc and gradients keyed by the reference checkpoint names."""
         params = self.trainable()
         for p in params.values():
             p.requires_grad_(True)
             p.grad = None
-        out = self.forward(batch, return_all=True)
+        out = self.forward(batch, return_all=True, lora_masks=lora_masks)
         out["loss"].backward()
         grads = {k: p.grad.detach().clone() for k, p in params.items()}
         if do_update:

@@ -492,6 +492,42 @@ __global__ void add_pos_kernel(bf16* __restrict__ x, const float* __restrict__ p
   }
 }
 
+// ---------------------------------------------------------------- LoRA-branch dropout (peft lora.Linear: lora_A(dropout(x)))
+// Counter-based mask: keep(i) = hash(seed, i) >= p * 2^32 — the same function regenerates the mask in the backward, so no
+// mask tensor is stored.  (The RNG stream differs from torch's Philox: only the distribution is reproduced.)
+__device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return static_cast<uint32_t>((z ^ (z >> 31)) >> 16);
+}
+// y = x * keep / (1 - p)
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n, uint32_t thresh, float inv_keep, uint64_t seed) {
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + i), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = mix32(seed, static_cast<uint64_t>(i + e)) >= thresh ? f[e] * inv_keep : 0.0f;
+    *reinterpret_cast<bf16x8*>(y + i) = pack8(f);
+  }
+}
+// out = base + lora * keep / (1 - p)   (dX of a LoRA linear under dropout: dY W + mask o ((dY sB) A))
+__global__ void dropout_bwd_add_kernel(const bf16* __restrict__ base, const bf16* __restrict__ lora, bf16* __restrict__ out, int64_t n, uint32_t thresh,
+                                       float inv_keep, uint64_t seed) {
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float fb[8], fl[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + i), fb);
+    unpack8(*reinterpret_cast<const bf16x8*>(lora + i), fl);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fb[e] += mix32(seed, static_cast<uint64_t>(i + e)) >= thresh ? fl[e] * inv_keep : 0.0f;
+    *reinterpret_cast<bf16x8*>(out + i) = pack8(fb);
+  }
+}
+
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics, single tensor, fp32)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                              float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_div) {
@@ -673,6 +709,24 @@ int slam_add_pos(void* x, const float* pos, int32_t batch, int32_t t, int32_t d,
   const int64_t total = static_cast<int64_t>(batch) * t * d / 8;
   add_pos_kernel<<<ew_grid(total, 1, 256), 256, 0, ST(stream)>>>(BF(x), pos, t, d, total);
   SLAM_LAUNCH_CHECK("slam_add_pos");
+  return 0;
+}
+static inline uint32_t drop_thresh(float p) {
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+}
+int slam_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
+  SLAM_CHECK_ARG(n % 8 == 0 && p >= 0.0f && p < 1.0f, "dropout: n %% 8 != 0 or p outside [0,1)");
+  if (n == 0) return 0;
+  dropout_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
+  SLAM_LAUNCH_CHECK("slam_dropout");
+  return 0;
+}
+int slam_dropout_bwd_add(const void* base, const void* lora, void* out, int64_t n, float p, uint64_t seed, void* stream) {
+  SLAM_CHECK_ARG(n % 8 == 0 && p >= 0.0f && p < 1.0f, "dropout_bwd_add: n %% 8 != 0 or p outside [0,1)");
+  if (n == 0) return 0;
+  dropout_bwd_add_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(base), CBF(lora), BF(out), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
+  SLAM_LAUNCH_CHECK("slam_dropout_bwd_add");
   return 0;
 }
 int slam_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,

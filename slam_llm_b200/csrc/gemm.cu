@@ -33,6 +33,7 @@ constexpr int GEMM_THREADS = 256;
 struct GemmKParams {
   int M, N;
   int kb1, kb2;
+  int ksplit, kb_per_split;   // split-K: work item = (tile, k-slice); partial tiles are merged with fp32 atomics
   int num_m_tiles, num_n_tiles;
   void* out;
   long long ldo;
@@ -118,7 +119,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // work items
   const int nkb = p.kb1 + p.kb2;
 
   if (warp == 0) {
@@ -133,15 +134,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       else tma_prefetch_l2_2d(&tmB2, (kb_pf - p.kb1) * GEMM_BK, n_tile_pf * BLOCK_N);
     };
     uint32_t kc = 0;
-    if (PF > 0 && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
+    if (PF > 0 && p.ksplit == 1 && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
       const int n_first = static_cast<int>(blockIdx.x) / p.num_m_tiles;
       for (int kb = 0; kb < PF && kb < nkb; ++kb) prefetch_b(n_first, kb);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      const int tile = item / p.ksplit;
+      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
+      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
-      const int next_tile = tile + gridDim.x;
-      for (int kb = 0; kb < nkb; ++kb, ++kc) {
+      const int next_tile = (PF > 0 && p.ksplit == 1) ? item + static_cast<int>(gridDim.x) : total_tiles;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++kc) {
         const uint32_t stage = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1u;
         mbar_wait(&empty_bar[stage], ph ^ 1u);
@@ -157,7 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(dA, &tmA2, &full_bar[stage], k2 * GEMM_BK, m_tile * BLOCK_M);
             tma_load_2d(dB, &tmB2, &full_bar[stage], k2 * GEMM_BK, n_tile * BLOCK_N);
           }
-          if (PF > 0) {
+          if (PF > 0 && p.ksplit == 1) {
             if (kb + PF < nkb) prefetch_b(n_tile, kb + PF);
             else if (next_tile < total_tiles) prefetch_b(next_tile / p.num_m_tiles, kb + PF - nkb);
           }
@@ -170,13 +174,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N);
     uint32_t kc = 0;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
+      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
+      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
       const uint32_t acc = it % ACC_STAGES;
       const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tempty_bar[acc], aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * HALVES * BLOCK_N;
-      for (int kb = 0; kb < nkb; ++kb, ++kc) {
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++kc) {
         const uint32_t stage = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1u;
         mbar_wait(&full_bar[stage], ph);
@@ -190,10 +196,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // the second M=128 half of a 256-row A tile starts 128 rows * 128 B = 16 KB further (+1024 units)
 #pragma unroll
             for (int hf = 0; hf < HALVES; ++hf)
-              umma_bf16(d_tmem + hf * BLOCK_N, a_desc + 1024u * hf + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem + hf * BLOCK_N, a_desc + 1024u * hf + 2u * k, b_desc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == kb_end - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
       }
@@ -202,7 +208,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------ epilogue
     const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
+      const int tile = item / p.ksplit;
       const int m_tile = tile % p.num_m_tiles;
       const int n_tile = tile / p.num_m_tiles;
       const uint32_t acc = it % ACC_STAGES;
@@ -264,7 +271,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
               v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
             }
-            if (p.out_f32) {
+            if (p.ksplit > 1) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) atomicAdd(o + e, v[e]);      // k-slices merge into the zero-initialised fp32 output
+            } else if (p.out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
               *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -375,7 +386,12 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   p.residual = reinterpret_cast<const bf16*>(g->residual);
   p.ldr = g->ldr;
   p.alpha = g->alpha;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  p.ksplit = g->split_k > 1 ? g->split_k : 1;
+  const int nkb_total = p.kb1 + p.kb2;
+  if (p.ksplit > nkb_total) p.ksplit = nkb_total;
+  p.kb_per_split = static_cast<int>(ceil_div(nkb_total, p.ksplit));
+  p.ksplit = static_cast<int>(ceil_div(nkb_total, p.kb_per_split));   // no empty k-slices
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tcgen05_kernel<BLOCK_M, BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   SLAM_LAUNCH_CHECK("slam_gemm_bf16");
@@ -423,6 +439,8 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
   SLAM_CHECK_ARG(g->bias == nullptr || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
+  SLAM_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && g->bias == nullptr && g->residual == nullptr && g->act == 0),
+                 "gemm: split_k needs a zero-initialised f32 output and no bias/activation/residual");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
   if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2);

@@ -32,6 +32,19 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch.Tensor:
+    """bf16 out = a @ b.T (+ a2 @ b2.T) for products with few output tiles but a long K (LoRA rank-64 products, lm_head dgrad):
+    split-K over otherwise idle SMs (fp32 atomics into a zeroed buffer), then one cast back to bf16."""
+    M, K = a.shape
+    N = b.shape[0]
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 64 else 1)
+    nkb = (K + 63) // 64 + ((a2.shape[1] + 63) // 64 if a2 is not None else 0)
+    split = min(8, nkb // 4, max(1, 148 // tiles))
+    if split <= 1:
+        return ops.gemm(a, b, a2=a2, b2=b2)
+    return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out_f32=True, split_k=split))
+
+
 def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
@@ -334,6 +347,11 @@ class LlamaLoRAB200:
                     arena.add(self._pname(m, "A"), (L, lora.r, in_f))      # lora_A.weight [r, in] stacked over layers
                     arena.add(self._pname(m, "Bt"), (L, lora.r, out_f))    # lora_B.weight^T [r, out] stacked over layers
         self.saved: Optional[dict] = None
+        # LoRA-branch dropout (peft lora_dropout): active only for training forwards when the owner enables it
+        self.dropout_p = float(lora.dropout) if lora is not None else 0.0
+        self.dropout_active = False
+        self.dropout_seed = seed
+        self.dropout_step = 0
 
     # names of the stacked arena tensors (the slam_llm mirror exposes them under the peft key names)
     @staticmethod
@@ -406,27 +424,42 @@ class LlamaLoRAB200:
         return self._rope_cache[S]
 
     # ---------------------------------------------------------------------------------------- linear (+LoRA) helpers
+    def _drop_seed(self, li: int, gname: str) -> int:
+        gi = list(GROUPS).index(gname)
+        return (self.dropout_seed * 1000003 + self.dropout_step * 4099 + li * 8 + gi) & 0x7FFFFFFFFFFFFFFF
+
     def _lin_fwd(self, x, w, gname: str, li: int, residual=None, out=None):
+        """y = x W^T (+ residual) + (dropout(x) A_cat^T)(s B_cat)^T  ->  (y, saved) with saved = (x_lora, T, seed) for the backward."""
         info = self.groups.get(gname)
         if info is None:
             return ops.gemm(x, w, residual=residual, out=out), None
-        t = ops.gemm(x, info["a_cat"][li])                                                 # T = x A_cat^T  [M, rpad]
-        return ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out), t   # fused base + LoRA tile
+        p, seed = self.dropout_p if self.dropout_active else 0.0, 0
+        x_lora = x
+        if p > 0.0:
+            seed = self._drop_seed(li, gname)
+            x_lora = ops.dropout(x, p, seed)                                             # lora_A(dropout(x)): LoRA branch only
+        t = _gemm_few_tiles(x_lora, info["a_cat"][li])                                   # T = x A_cat^T  [M, rpad]
+        y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out)       # fused base + LoRA tile
+        return y, (x_lora, t, p, seed)
 
-    def _lin_bwd(self, dy, wT, gname: str, li: int, x_in, t):
-        """dX = dY W + (dY B_s) A  and LoRA grads (dA = U^T x, dB^T = s T^T dY) into the arena."""
+    def _lin_bwd(self, dy, wT, gname: str, li: int, saved):
+        """dX = dY W + mask o ((dY sB) A)  and LoRA grads (dA = U^T x_lora, dB^T = s T^T dY) into the arena."""
         info = self.groups.get(gname)
         if info is None:
             return ops.gemm(dy, wT)
-        u = ops.gemm(dy, info["b_catT"][li])                                               # U = dY (s B)  [M, rpad]
-        dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li])
+        x_lora, t, p, seed = saved
+        u = _gemm_few_tiles(dy, info["b_catT"][li])                                      # U = dY (s B)  [M, rpad]
+        if p > 0.0:
+            dx = ops.dropout_bwd_add(ops.gemm(dy, wT), ops.gemm(u, info["a_catT"][li]), p, seed)
+        else:
+            dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li])                           # fused: one accumulator tile
         r, s = self.lora.r, self.lora.scaling
         for m in info["targets"]:
             off, col = info["roff"][m], info["cols"][m]
             out_f = linear_shape(self.cfg, m)[0]
             gA = self.arena.view(self._pname(m, "A"), "grad")[li]
             gBt = self.arena.view(self._pname(m, "Bt"), "grad")[li]
-            ops.wgrad_thin(u[:, off: off + r], x_in, gA)
+            ops.wgrad_thin(u[:, off: off + r], x_lora, gA)
             ops.wgrad_thin(t[:, off: off + r], dy[:, col: col + out_f], gBt, scale=s)
         return dx
 
@@ -443,7 +476,7 @@ class LlamaLoRAB200:
         saved_layers = []
         for li, Lw in enumerate(self.layers):
             xn1, rstd1 = ops.rmsnorm_fwd(x, Lw["ln1"], cfg.eps, need_rstd=save)
-            qkv, t_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li)
+            qkv, sv_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li)
             ops.rope_(qkv[:, :Dq], H, dh, S, cos, sin)
             ops.rope_(qkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin)
             q = qkv[:, :Dq].view(B, S, H, dh)
@@ -451,22 +484,14 @@ class LlamaLoRAB200:
             v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
             attn, lse = ops.attn_fwd(q, k, v, causal=True, scale=scale, key_mask=key_mask, need_lse=save)
             attn2 = attn.view(M, Dq)
-            x2, t_o = self._lin_fwd(attn2, Lw["wo"], "o", li, residual=x)
+            x2, sv_o = self._lin_fwd(attn2, Lw["wo"], "o", li, residual=x)
             xn2, rstd2 = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=save)
-            gu, t_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
+            gu, sv_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
             hmid = ops.swiglu_fwd(gu)
-            x3, t_d = self._lin_fwd(hmid, Lw["wd"], "down", li, residual=x2)
+            x3, sv_d = self._lin_fwd(hmid, Lw["wd"], "down", li, residual=x2)
             if save:
-                keep = dict(x=x, rstd1=rstd1, qkv=qkv, attn=attn, lse=lse, x2=x2, rstd2=rstd2, gu=gu)
-                if "qkv" in self.groups:
-                    keep.update(xn1=xn1, t_qkv=t_qkv)
-                if "o" in self.groups:
-                    keep.update(t_o=t_o)
-                if "gu" in self.groups:
-                    keep.update(xn2=xn2, t_gu=t_gu)
-                if "down" in self.groups:
-                    keep.update(hmid=hmid, t_d=t_d)
-                saved_layers.append(keep)
+                saved_layers.append(dict(x=x, rstd1=rstd1, qkv=qkv, attn=attn, lse=lse, x2=x2, rstd2=rstd2, gu=gu,
+                                         sv_qkv=sv_qkv, sv_o=sv_o, sv_gu=sv_gu, sv_d=sv_d))
             x = x3
         xf, rstd_f = ops.rmsnorm_fwd(x, self.norm, cfg.eps, need_rstd=save)
         if save:
@@ -487,12 +512,12 @@ class LlamaLoRAB200:
         for li in range(cfg.layers - 1, -1, -1):
             Lw, kp = self.layers[li], sv["layers"][li]
             # ---- MLP block: x3 = x2 + down(silu(g) * u)
-            dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp.get("hmid"), kp.get("t_d"))
+            dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
             dgu = ops.swiglu_bwd(kp["gu"], dhmid)
-            dxn2 = self._lin_bwd(dgu, Lw["wguT"], "gu", li, kp.get("xn2"), kp.get("t_gu"))
+            dxn2 = self._lin_bwd(dgu, Lw["wguT"], "gu", li, kp["sv_gu"])
             dx2 = ops.rmsnorm_bwd(dxn2, kp["x2"], Lw["ln2"], kp["rstd2"], dres=dx)
             # ---- attention block: x2 = x + o(attn(rope(qkv(norm(x)))))
-            dattn = self._lin_bwd(dx2, Lw["woT"], "o", li, kp["attn"].view(M, Dq), kp.get("t_o"))
+            dattn = self._lin_bwd(dx2, Lw["woT"], "o", li, kp["sv_o"])
             qkv = kp["qkv"]
             q = qkv[:, :Dq].view(B, S, H, dh)
             k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
@@ -502,7 +527,7 @@ class LlamaLoRAB200:
                          dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh))
             ops.rope_(dqkv[:, :Dq], H, dh, S, cos, sin, inverse=True)
             ops.rope_(dqkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin, inverse=True)
-            dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp.get("xn1"), kp.get("t_qkv"))
+            dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp["sv_qkv"])
             dx = ops.rmsnorm_bwd(dxn1, kp["x"], Lw["ln1"], kp["rstd1"], dres=dx2)
             sv["layers"][li] = None
         return dx.view(B, S, cfg.d)
@@ -541,6 +566,7 @@ class SlamStepB200:
         self.filters_t = mel_filterbank(self.enc_cfg.n_mels).t().contiguous().to(device)
         self._ctx = None
         self.micro_steps = 0   # backward() calls since the last optimizer step (gradient accumulation)
+        self.lora_dropout_enabled = True   # module.train()/eval() of the host mirror toggles this (reference quirk Q6)
 
     # ------------------------------------------------------------------ state dict in the reference's key names
     def trainable_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
@@ -595,6 +621,8 @@ class SlamStepB200:
             mel = mel.to(dev, F32)
         B, S = ids.shape
         self.llm.pack_lora()                                                               # adapters change every optimizer step
+        self.llm.dropout_active = bool(train and self.lora_dropout_enabled and self.llm.dropout_p > 0.0)
+        self.llm.dropout_step += 1
         enc_out = self.encoder.forward(mel)
         aud = self.projector.forward(enc_out, save=train)
         x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
@@ -631,7 +659,7 @@ class SlamStepB200:
         dlogits = torch.empty((R, V), device=dev, dtype=BF16)
         scratch = (torch.zeros(1, device=dev), torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, device=dev, dtype=torch.int32))
         ops.cross_entropy(logits, c["tgts"], scratch, dlogits, gs)
-        dh = ops.gemm(dlogits, self.llm.lm_headT)                                          # [R, D]
+        dh = _gemm_few_tiles(dlogits, self.llm.lm_headT)                                   # [R, D], K = vocab: split-K
         M = c["B"] * c["S"]
         if c["full"]:
             dxf = dh

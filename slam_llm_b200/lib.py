@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("alpha", _f32),
         ("m", _i32), ("n", _i32),
         ("block_n", _i32),
+        ("split_k", _i32),
     ]
 
 
@@ -75,6 +76,8 @@ _SIGS = {
     "slam_rope": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "slam_swiglu_fwd": [_vp, _vp, _i32, _i32, _vp],
     "slam_swiglu_bwd": [_vp, _vp, _vp, _i32, _i32, _vp],
+    "slam_dropout": [_vp, _vp, _i64, _f32, C.c_uint64, _vp],
+    "slam_dropout_bwd_add": [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp],
     "slam_cross_entropy": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "slam_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     "slam_cast_f32_to_bf16": [_vp, _vp, _i64, _f32, _vp],

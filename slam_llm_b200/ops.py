@@ -55,12 +55,16 @@ def set_gemm_event_log(log) -> None:
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0) -> torch.Tensor:
+         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1) -> torch.Tensor:
     """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16."""
     _req(a, BF16, "gemm.a"); _req(b, BF16, "gemm.b")
     M, K1 = a.shape
     N = b.shape[0]
     assert b.shape[1] == K1, (a.shape, b.shape)
+    if split_k > 1:
+        assert out_f32 and bias is None and residual is None and act == 0, "split_k needs a plain f32 output"
+        if out is None:
+            out = torch.zeros((M, N), device=a.device, dtype=F32)          # k-slices are merged with atomics
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=F32 if out_f32 else BF16)
     g = _l.GemmArgs()
@@ -93,6 +97,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     g.alpha = alpha
     g.m, g.n = M, N
     g.block_n = block_n
+    g.split_k = split_k
     if _GEMM_LOG is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -298,6 +303,27 @@ def swiglu_bwd(gu, dh, out=None):
     if out is None:
         out = torch.empty_like(gu)
     _l.check(_l.load().slam_swiglu_bwd(gu.data_ptr(), dh.data_ptr(), out.data_ptr(), rows, f2 // 2, _stream()), "slam_swiglu_bwd")
+    return out
+
+
+def dropout(x, p: float, seed: int, out=None):
+    """y = x * keep/(1-p); keep regenerated from (seed, element index) — see dropout_bwd_add."""
+    _req(x, BF16, "dropout.x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(_l.load().slam_dropout(x.data_ptr(), out.data_ptr(), x.numel(), p, seed, _stream()), "slam_dropout")
+    return out
+
+
+def dropout_bwd_add(base, lora, p: float, seed: int, out=None):
+    """out = base + lora * keep/(1-p) with the mask of dropout(seed)."""
+    _req(base, BF16, "dropout_bwd_add.base"); _req(lora, BF16, "dropout_bwd_add.lora")
+    assert base.is_contiguous() and lora.is_contiguous() and base.numel() == lora.numel()
+    if out is None:
+        out = torch.empty_like(base)
+    _l.check(_l.load().slam_dropout_bwd_add(base.data_ptr(), lora.data_ptr(), out.data_ptr(), base.numel(), p, seed, _stream()),
+             "slam_dropout_bwd_add")
     return out
 
 

@@ -195,8 +195,6 @@ def setup_llm(train_config, model_config, **kwargs):
         raise NotImplementedError("peft_ckpt directories: pass the trainable-only model.pt via ckpt_path instead")
     cfg = _load_llm_cfg(model_config.llm_path)
     lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
-    if lora_cfg is not None and lora_cfg.dropout > 0:
-        logger.warning(f"lora_dropout={lora_cfg.dropout} is treated as 0 on the B200 path (dropout on the LoRA branch is not implemented yet)")
     model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, bool(train_config.use_peft))
     print_module_size(model, model_config.llm_name, _rank(train_config))
     model.eval()
@@ -315,6 +313,7 @@ class slam_model(nn.Module):
         if kwargs.get("inference_mode", False):
             return self._inputs_embeds(batch), attention_mask
         train = torch.is_grad_enabled() and labels is not None
+        self.b200.lora_dropout_enabled = self.training        # model.train() re-enables LoRA dropout each epoch (reference quirk Q6)
         full = (not train) or bool(self.train_config.get("b200_full_logits", False))
         loss, acc, logits = self.b200.forward(batch, train=train, full_logits=full)
         if train:

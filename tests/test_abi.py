@@ -33,14 +33,14 @@ def test_struct_layout_matches_c_compiler(lib, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slam_b200.h"\nint main(){\n'
                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(slam_gemm_args), offsetof(slam_gemm_args, out), offsetof(slam_gemm_args, alpha), '
-                   'offsetof(slam_gemm_args, block_n), offsetof(slam_gemm_args, k2));\n'
+                   'offsetof(slam_gemm_args, split_k), offsetof(slam_gemm_args, k2));\n'
                    'printf("%zu %zu %zu %zu\\n", sizeof(slam_attn_args), offsetof(slam_attn_args, scale), offsetof(slam_attn_args, dout), '
                    'offsetof(slam_attn_args, dkv_part));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
     g, a = lib.GemmArgs, lib.AttnArgs
-    assert [int(x) for x in out[:5]] == [ctypes.sizeof(g), g.out.offset, g.alpha.offset, g.block_n.offset, g.k2.offset]
+    assert [int(x) for x in out[:5]] == [ctypes.sizeof(g), g.out.offset, g.alpha.offset, g.split_k.offset, g.k2.offset]
     assert [int(x) for x in out[5:]] == [ctypes.sizeof(a), a.scale.offset, a.dout.offset, a.dkv_part.offset]
 
 

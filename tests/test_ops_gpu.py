@@ -94,6 +94,16 @@ def test_gemm_dual_segment_lora(ops, tile):
     assert rel_err(only_base, ref) > 2e-2  # the second segment really contributes
 
 
+@pytest.mark.parametrize("M,N,K,K2,split", [(1600, 64, 4096, 0, 8), (308, 4096, 12800, 0, 3), (1600, 64, 6144, 64, 5), (257, 512, 640, 0, 4)])
+def test_gemm_split_k(ops, M, N, K, K2, split):
+    a, b = rnd(M, K, seed=60), rnd(N, K, scale=0.05, seed=61)
+    a2 = rnd(M, K2, seed=62) if K2 else None
+    b2 = rnd(N, K2, scale=0.05, seed=63) if K2 else None
+    out = ops.gemm(a, b, a2=a2, b2=b2, out_f32=True, split_k=split)
+    ref = a.float() @ b.float().t() + (a2.float() @ b2.float().t() if K2 else 0)
+    assert rel_err(out, ref) < 1e-4           # fp32 accumulation, only the summation order differs
+
+
 def test_gemm_strided_views(ops):
     # operands / outputs that are column slices of wider buffers (fused QKV style)
     M, K = 384, 512

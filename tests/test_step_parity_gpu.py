@@ -34,7 +34,7 @@ def build_pair(enc_cfg, llm_cfg, lora_cfg, proj_cfg, seed=42):
     from slam_llm_b200.engine import SlamStepB200
     om = round_frozen(so.OracleModel.build(enc_cfg, llm_cfg, lora_cfg, proj_cfg, seed=seed))
     eng = SlamStepB200(C.EncoderCfg(**vars(enc_cfg)), C.LlmCfg(**vars(llm_cfg)),
-                       C.LoraCfg(lora_cfg.r, lora_cfg.alpha, tuple(lora_cfg.targets)) if lora_cfg else None, C.ProjCfg(**vars(proj_cfg)),
+                       C.LoraCfg(lora_cfg.r, lora_cfg.alpha, tuple(lora_cfg.targets), lora_cfg.dropout) if lora_cfg else None, C.ProjCfg(**vars(proj_cfg)),
                        device="cuda:0", enc_weights=om.enc_w, llm_weights=om.llm_w, lora_weights=om.lora_w, proj_weights=om.proj_w)
     return om, eng
 
@@ -99,6 +99,47 @@ def test_step_matches_oracle(name):
         upd, upd_ref = (after[k] - before[k]).cpu(), new_ref[k].detach() - before[k].cpu()
         # first Adam step ~ -lr * sign(g): near-zero gradient elements may flip sign under bf16 noise, so the bar is on direction only
         assert cosine(upd, upd_ref) > 0.95, (k, cosine(upd, upd_ref))
+
+
+def test_lora_dropout_matches_oracle_given_the_same_masks():
+    """lora_dropout > 0: the kernels draw the mask from a counter-based hash (not torch's Philox), so the masks the step
+    used are regenerated with the same seeds and handed to the oracle; loss and gradients must then agree as usual."""
+    from slam_llm_b200 import ops
+    from slam_llm_b200.engine import GROUPS
+    c = CASES["tiny_dh64"]
+    lora = so.LoraCfg(8, 32, ("q_proj", "v_proj", "down_proj"), dropout=0.25)
+    om, eng = build_pair(c["enc"], c["llm"], lora, c["proj"])
+    assert eng.llm.dropout_p == 0.25
+    batch = so.synthetic_batch(2, 32000, c["llm"].vocab, prompt_len=6, answer_len=9, left_pad=[0, 3], seed=21)
+    loss, acc, _ = eng.forward(to_dev(batch), train=True)
+    masks = {}
+    B, S = batch["input_ids"].shape
+    for li, kp in enumerate(eng.llm.saved["layers"]):
+        for gname, members in GROUPS.items():
+            sv = kp["sv_" + {"qkv": "qkv", "o": "o", "gu": "gu", "down": "d"}[gname]]
+            if sv is None:
+                continue
+            x_lora, t, p, seed = sv
+            assert p == 0.25
+            m = ops.dropout(torch.ones_like(x_lora), p, seed).float().cpu()            # keep / (1 - p)
+            frac = (m > 0).float().mean().item()
+            assert abs(frac - 0.75) < 0.02 and set(m.unique().tolist()) <= {0.0, pytest.approx(1 / 0.75, rel=1e-2)}
+            mod = "self_attn" if gname in ("qkv", "o") else "mlp"
+            for name in members:
+                masks[f"model.layers.{li}.{mod}.{name}."] = m.view(B, S, -1)
+    eng.backward()
+    ref = om.step(dict(batch), do_update=False, lora_masks=masks)
+    assert abs(loss.item() - ref["loss"].item()) / ref["loss"].item() < 5e-3
+    grads = eng.trainable_state("grad")
+    gmax = max(g.norm().item() for g in ref["grads"].values())
+    for k, g_ref in ref["grads"].items():
+        if g_ref.norm().item() < 1e-3 * gmax:
+            continue
+        assert cosine(grads[k], g_ref) > 0.99 and rel_l2(grads[k], g_ref) < 3e-2, (k, cosine(grads[k], g_ref), rel_l2(grads[k], g_ref))
+    # eval forwards (train=False) and a disabled owner never drop
+    loss_eval, _, _ = eng.forward(to_dev(batch), train=False)
+    ref_eval = om.forward(dict(batch), return_all=True)
+    assert abs(loss_eval.item() - ref_eval["loss"].item()) / ref_eval["loss"].item() < 5e-3
 
 
 def test_full_logits_eval_path_matches_oracle():
