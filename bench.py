@@ -269,9 +269,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # ---------------- timed region 1: inputs resident in HBM; per-GEMM events for the roofline
-    gemm_log = []
-    ops.set_gemm_event_log(gemm_log)
+    # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -284,7 +282,6 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = ops.launch_count() - l0
-    ops.set_gemm_event_log(None)
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -293,9 +290,22 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * audio_s / (ms_per_step / 1e3)
+    final_loss = loss.item()
+    # ---------------- the same K steps again with a CUDA-event pair around every GEMM launch (roofline of the GEMM family);
+    # kept out of the `value` region because ~900 extra event records per step cost ~3 % of host time
+    gemm_log = []
+    ops.set_gemm_event_log(gemm_log)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        step_resident()
+    g1.record()
+    barrier()
+    ops.set_gemm_event_log(None)
+    ms_instr = g0.elapsed_time(g1)
     gemm_flops = sum(f for f, _, _ in gemm_log)
     gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_log)
-    final_loss = loss.item()
 
     # ---------------- timed region 2: end to end from pinned host buffers
     for _ in range(2):
@@ -323,7 +333,8 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step: base, fused LoRA, dgrad, wgrad, lm_head)",
             "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
             "peak_source": peak_src, "gemm_launches_per_step": len(gemm_log) // args.steps,
-            "gemm_time_share_of_step": round(gemm_ms / ms, 4), "step_algorithmic_tflop": round(fl["total"] / 1e12, 2),
+            "gemm_time_share_of_step": round(gemm_ms / ms_instr, 4),
+            "measured_over": f"{args.steps} instrumented steps (CUDA events around every GEMM launch) run right after the timed region", "step_algorithmic_tflop": round(fl["total"] / 1e12, 2),
             "step_achieved_tflops": round(fl["total"] / (ms_per_step / 1e3) / 1e12, 1)}
     traffic_file = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(traffic_file):

@@ -7,6 +7,7 @@
 // Round-1 implementation: warp-level mma.sync.m16n8k16 tensor-core tiles with ldmatrix-fed
 // fragments (attention is ~1.5 % of decoder FLOPs at S≈400; the tcgen05 path is reserved for the GEMMs).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "../../include/slam_b200.h"
 #include "common.cuh"
@@ -603,12 +604,24 @@ static int launch_bwd(const AttnP& p, cudaStream_t st) {
 
 }  // namespace slam
 
+namespace slam {
+int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st);   // fmha_tc.cu: 0 = launched, 1 = shape not handled, else error
+}
+
 extern "C" int slam_attn_fwd(const slam_attn_args* a, void* stream) {
   using namespace slam;
   AttnP p;
   int rc = fill_params(a, p, false);
   if (rc != 0) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool use_tc = []() {
+    const char* e = getenv("SLAM_ATTN_TC");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (use_tc) {
+    rc = fmha_fwd_tc_try(a, st);       // tcgen05 / TMEM kernel for the encoder shape (dh = 64, non-causal, unmasked)
+    if (rc != 1) return rc;
+  }
   if (a->dh == 128) return launch_fwd<128, 1>(p, st);
   // MT = 2 (32 rows per warp) measured SLOWER on B200 (324 us vs 261 us per whisper-large-v3 layer: 255 registers, 8 warps/SM);
   // it stays instantiated for experiments behind SLAM_ATTN_MT2.

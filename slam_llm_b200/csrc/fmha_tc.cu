@@ -1,0 +1,368 @@
+// tcgen05 / TMEM flash-attention forward for the Whisper encoder (dh = 64, non-causal, no mask) — the sm_100a replacement of the
+// mma.sync kernel in attention.cu for that shape (whisper qkv_attention via models/encoder.py:26-27).
+//
+// One CTA = 128 query rows of one (batch, head); the key/value sequence is walked in tiles of 128 keys.
+//   warp 0      TMA producer: Q tile once, then K and V tiles (128 x 64 bf16, 128B swizzle) through 2-stage rings
+//   warp 1      MMA issuer (one lane):  S_j = Q K_j^T  (M=128, N=128, K=64)  into one of two TMEM score buffers,
+//                                       O  += P_j V_j  (M=128, N=64,  K=128) with P_j read from shared memory (K-major) and
+//                                       V_j used in place as an MN-major operand (no transposed copy of V)
+//   warp 2      TMEM allocation (2 x 128 score columns + 64 output columns)
+//   warps 4-7   softmax: thread = query row; tcgen05.ld of the score row, online max / exp2 / sum in fp32, bf16 P written to
+//               shared memory in the UMMA 128B-swizzled K-major layout, O rescaled in TMEM (tcgen05.ld/st) when the running
+//               max moves; final O / l written to global memory.
+// S_{j+1} is issued before P_j V_j, so the tensor pipe computes the next scores while the softmax warps work on the current tile.
+#include <math_constants.h>
+
+#include "../../include/slam_b200.h"
+#include "common.cuh"
+#include "host.cuh"
+
+namespace slam {
+
+constexpr int FA_BM = 128;   // query rows per CTA
+constexpr int FA_BN = 128;   // keys per tile
+constexpr int FA_DH = 64;
+constexpr int FA_THREADS = 256;
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;          // one 128 x 64 bf16 tile (Q, K_j, V_j, half of P_j)
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 + 2 + 4) + 256 + 1024;
+
+struct FmhaParams {
+  int sq, sk, hq;
+  float scale_log2;
+  bf16* out;
+  long long ldo;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor: rows of the tile run along K (8-row groups 1024 B apart = SBO),
+// 64 contiguous bf16 (128 B) along the MN dimension.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;              // LBO: distance between 64-element MN blocks (single block here)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;      // SBO: distance between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// D=f32, A=bf16 K-major, B=bf16 with selectable major-ness
+__host__ __device__ constexpr uint32_t fa_idesc(uint32_t M, uint32_t N, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_TILE_BYTES;                  // 2 stages
+  uint8_t* sV = sK + 2 * FA_TILE_BYTES;              // 2 stages
+  uint8_t* sP = sV + 2 * FA_TILE_BYTES;              // 2 buffers x 2 K-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * FA_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* pv_done = bars + 15;  // [2]  P buffer free again / O stable after P_j V_j
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * FA_BM;
+  const int n_tiles = (p.sk + FA_BN - 1) / FA_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&pv_done[s], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;           // output accumulator: columns [256, 320)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, h * FA_DH, b * p.sq + q0);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1u;
+      mbar_wait(&k_empty[st], ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&k_full[st], FA_TILE_BYTES);
+        tma_load_2d(sK + st * FA_TILE_BYTES, &tmK, &k_full[st], h * FA_DH, b * p.sk + j * FA_BN);
+      }
+      mbar_wait(&v_empty[st], ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[st], FA_TILE_BYTES);
+        tma_load_2d(sV + st * FA_TILE_BYTES, &tmV, &v_full[st], h * FA_DH, b * p.sk + j * FA_BN);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = fa_idesc(128, FA_BN, 0);      // S = Q K^T : both operands K-major
+    constexpr uint32_t idesc_o = fa_idesc(128, FA_DH, 1);      // O += P V  : V is MN-major
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1u;
+      mbar_wait(&k_full[st], ph);
+      mbar_wait(&s_empty[st], ph ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sQ));
+        const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + st * FA_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_DH / 16; ++k) umma_bf16(tmem_base + st * FA_BN, a_desc + 2u * k, b_desc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1u;
+      if (j + 1 < n_tiles) issue_s(j + 1);
+      mbar_wait(&p_full[st], ph);
+      mbar_wait(&v_full[st], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV + st * FA_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) {
+          // A = P: K-block k/4 (16 KB apart), 32 B per k-step inside it; B = V: 16 keys = two 8-row groups = 2048 B per k-step
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sP + (st * 2 + (k >> 2)) * FA_TILE_BYTES)) + 2u * (k & 3);
+          umma_bf16(tmem_o, a_desc, v_desc + 128u * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[st]);
+        if (j == n_tiles - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
+    const int qd = warp - 4;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    float m_run = -CUDART_INF_F, l_run = 0.0f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1u;
+      const int n0 = j * FA_BN;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + st * FA_BN + lane_base;
+      const bool tail = n0 + FA_BN > p.sk;
+      // pass 1: row maximum (log2 domain)
+      float mx = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]) * p.scale_log2;
+          if (tail && n0 + c * 32 + e >= p.sk) v = -CUDART_INF_F;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = ex2_approx(m_run - m_new);          // 0 on the first tile (m_run = -inf)
+      const bool moved = m_new > m_run;
+      m_run = m_new;
+      // the P buffer of this parity was last read by P_{j-2} V_{j-2}
+      if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1u);
+      // pass 2: p = exp2(s - m), row sum, bf16 P into the swizzled K-major shared tile
+      float rs = 0.0f;
+      uint8_t* prow = sP + st * 2 * FA_TILE_BYTES + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + c * 32, r);
+        tmem_ld_wait();
+        if (c == FA_BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[st]);            // scores are in registers: the MMA warp may overwrite this buffer
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float v0 = __uint_as_float(r[2 * e]) * p.scale_log2 - m_new;
+          float v1 = __uint_as_float(r[2 * e + 1]) * p.scale_log2 - m_new;
+          float p0 = ex2_approx(v0), p1 = ex2_approx(v1);
+          if (tail) {
+            if (n0 + c * 32 + 2 * e >= p.sk) p0 = 0.0f;
+            if (n0 + c * 32 + 2 * e + 1 >= p.sk) p1 = 0.0f;
+          }
+          rs += p0 + p1;
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        // 32 keys = 4 chunks of 16 B; chunk index inside the 64-key K-block is XOR-swizzled with (row % 8)
+        uint8_t* kblock = prow + (c >> 1) * FA_TILE_BYTES;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+          *reinterpret_cast<uint4*>(kblock + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+      }
+      l_run = l_run * corr + rs;
+      // rescale the running output when any row of this warp raised its maximum (needs P_{j-1} V_{j-1} complete)
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < FA_DH / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_o + lane_base + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * corr);
+          tmem_st_32x32(tmem_o + lane_base + c * 32, r);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async();            // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    }
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+    const int grow = q0 + row;
+#pragma unroll 1
+    for (int c = 0; c < FA_DH / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_o + lane_base + c * 32, r);
+      tmem_ld_wait();
+      if (grow < p.sq) {
+        bf16* o = p.out + (static_cast<long long>(b) * p.sq + grow) * p.ldo + h * FA_DH + c * 32;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(r[8 * e]) * inv, __uint_as_float(r[8 * e + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(r[8 * e + 2]) * inv, __uint_as_float(r[8 * e + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(r[8 * e + 4]) * inv, __uint_as_float(r[8 * e + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(r[8 * e + 6]) * inv, __uint_as_float(r[8 * e + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + 8 * e) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*PFN_encodeTiledF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int fa_make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld) {
+  static PFN_encodeTiledF enc = nullptr;
+  if (enc == nullptr) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      set_error("fmha: cuTensorMapEncodeTiled unavailable");
+      return -2;
+    }
+    enc = reinterpret_cast<PFN_encodeTiledF>(fp);
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("fmha: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    return -3;
+  }
+  return 0;
+}
+
+// Returns 1 if the shape is not handled by the tcgen05 kernel (caller falls through to the mma.sync kernel), 0 on success.
+int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
+  if (a->dh != 64 || a->causal || a->key_mask != nullptr || a->lse != nullptr || a->hq != a->hkv || a->sq != a->sk || a->sk < 128) return 1;
+  if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->k) & 15) || (reinterpret_cast<uintptr_t>(a->v) & 15)) return 1;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) {
+      set_error("fmha: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  const long long rows_q = static_cast<long long>(a->batch) * a->sq, rows_k = static_cast<long long>(a->batch) * a->sk;
+  int rc;
+  if ((rc = fa_make_tmap(&tq, a->q, rows_q, static_cast<long long>(a->hq) * 64, a->ldq)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tk, a->k, rows_k, static_cast<long long>(a->hkv) * 64, a->ldk)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tv, a->v, rows_k, static_cast<long long>(a->hkv) * 64, a->ldv)) != 0) return rc;
+  FmhaParams p;
+  p.sq = a->sq;
+  p.sk = a->sk;
+  p.hq = a->hq;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.ldo = a->ldo;
+  dim3 grid(static_cast<unsigned>(ceil_div(a->sq, FA_BM)), a->hq, a->batch);
+  fmha_fwd_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, p);
+  SLAM_LAUNCH_CHECK("slam_attn_fwd.tcgen05");
+  return 0;
+}
+
+}  // namespace slam

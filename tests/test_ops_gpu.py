@@ -271,6 +271,18 @@ def test_attention_fwd_bwd(ops, B, S, Hq, Hkv, dh, causal, masked):
         assert cos_sim(got, want) > 0.999, (name, cos_sim(got, want))
 
 
+@pytest.mark.parametrize("B,S,H", [(2, 1500, 6), (1, 333, 20), (4, 1500, 20), (3, 128, 2), (1, 129, 1), (2, 1000, 8)])
+def test_attention_encoder_tcgen05(ops, B, S, H):
+    """Whisper-encoder shape (dh = 64, non-causal, unmasked, no lse): served by the tcgen05/TMEM kernel (fmha_tc.cu)."""
+    d = H * 64
+    qkv = rnd(B * S, 3 * d, seed=70)
+    q, k, v = (qkv[:, i * d:(i + 1) * d].view(B, S, H, 64) for i in range(3))
+    out, _ = ops.attn_fwd(q, k, v, causal=False, scale=0.125)
+    ref = _ref_attn(q, k, v, False, 0.125, None)
+    assert rel_err(out, ref) < 1.5e-2, rel_err(out, ref)
+    assert cos_sim(out, ref) > 0.9995
+
+
 # ----------------------------------------------------------------------------------------------- merge
 def _ref_merge(ids, mask, audio, embed):
     ids = ids.clone()
