@@ -191,7 +191,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int qd = warp - 4;
     const int row = qd * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    float m_run = -CUDART_INF_F, l_run = 0.0f;
+    float m_run = -CUDART_INF_F, l_run = 0.0f;     // running max in the scaled log2 domain
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1u;
@@ -199,61 +199,62 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
       const uint32_t ts = tmem_base + st * FA_BN + lane_base;
-      const bool tail = n0 + FA_BN > p.sk;
-      // pass 1: row maximum (log2 domain)
-      float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + c * 32, r);
-        tmem_ld_wait();
+      // the whole 128-wide score row lives in registers: one TMEM round trip per tile, and the score buffer is handed back
+      // to the MMA warp before any math
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32(ts, s0);
+      tmem_ld_32x32(ts + 32, s1);
+      tmem_ld_32x32(ts + 64, s2);
+      tmem_ld_32x32(ts + 96, s3);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (n0 + FA_BN > p.sk) {                       // key tail: columns >= sk never contribute
+        const uint32_t ninf = __float_as_uint(-CUDART_INF_F);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float v = __uint_as_float(r[e]) * p.scale_log2;
-          if (tail && n0 + c * 32 + e >= p.sk) v = -CUDART_INF_F;
-          mx = fmaxf(mx, v);
+          if (n0 + e >= p.sk) s0[e] = ninf;
+          if (n0 + 32 + e >= p.sk) s1[e] = ninf;
+          if (n0 + 64 + e >= p.sk) s2[e] = ninf;
+          if (n0 + 96 + e >= p.sk) s3[e] = ninf;
         }
       }
-      const float m_new = fmaxf(m_run, mx);
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float corr = ex2_approx(m_run - m_new);          // 0 on the first tile (m_run = -inf)
       const bool moved = m_new > m_run;
       m_run = m_new;
       // the P buffer of this parity was last read by P_{j-2} V_{j-2}
       if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1u);
-      // pass 2: p = exp2(s - m), row sum, bf16 P into the swizzled K-major shared tile
+      // p = exp2(s * scale - m): one FFMA + one MUFU per element; bf16 P into the swizzled K-major shared tile
       float rs = 0.0f;
       uint8_t* prow = sP + st * 2 * FA_TILE_BYTES + row * 128;
-#pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + c * 32, r);
-        tmem_ld_wait();
-        if (c == FA_BN / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[st]);            // scores are in registers: the MMA warp may overwrite this buffer
-        }
+      const float neg_m = -m_new;
+      auto emit = [&](const uint32_t (&sv)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          float v0 = __uint_as_float(r[2 * e]) * p.scale_log2 - m_new;
-          float v1 = __uint_as_float(r[2 * e + 1]) * p.scale_log2 - m_new;
-          float p0 = ex2_approx(v0), p1 = ex2_approx(v1);
-          if (tail) {
-            if (n0 + c * 32 + 2 * e >= p.sk) p0 = 0.0f;
-            if (n0 + c * 32 + 2 * e + 1 >= p.sk) p1 = 0.0f;
-          }
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), p.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), p.scale_log2, neg_m));
           rs += p0 + p1;
           pk[e] = pack_bf16x2(p0, p1);
         }
-        // 32 keys = 4 chunks of 16 B; chunk index inside the 64-key K-block is XOR-swizzled with (row % 8)
+        // 32 keys = 4 chunks of 16 B; the chunk index inside the 64-key K-block is XOR-swizzled with (row % 8)
         uint8_t* kblock = prow + (c >> 1) * FA_TILE_BYTES;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
           *reinterpret_cast<uint4*>(kblock + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
-      }
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
       l_run = l_run * corr + rs;
       // rescale the running output when any row of this warp raised its maximum (needs P_{j-1} V_{j-1} complete)
       if (j > 0 && __any_sync(0xffffffffu, moved)) {
