@@ -2,12 +2,12 @@
 // mma.sync kernel in attention.cu for that shape (whisper qkv_attention via models/encoder.py:26-27).
 //
 // One CTA = 128 query rows of one (batch, head); the key/value sequence is walked in tiles of 128 keys.
-//   warp 0      TMA producer: Q tile once, then K and V tiles (128 x 64 bf16, 128B swizzle) through 2-stage rings
+//   warp 0      TMA producer: Q tile once, then K (2-stage ring) and V tiles (128 x 64 bf16, 128B swizzle)
 //   warp 1      MMA issuer (one lane):  S_j = Q K_j^T  (M=128, N=128, K=64)  into one of two TMEM score buffers,
 //                                       O  += P_j V_j  (M=128, N=64,  K=128) with P_j read from shared memory (K-major) and
 //                                       V_j used in place as an MN-major operand (no transposed copy of V)
-//   warp 2      TMEM allocation (2 x 128 score columns + 64 output columns)
-//   warps 4-7   softmax: thread = query row; tcgen05.ld of the score row, online max / exp2 / sum in fp32, bf16 P written to
+//               (warp 1 also allocates the CTA's 256 TMEM columns: 128 score + 64 output used; two CTAs share an SM)
+//   warps 2-5   softmax: thread = query row; tcgen05.ld of the score row, online max / exp2 / sum in fp32, bf16 P written to
 //               shared memory in the UMMA 128B-swizzled K-major layout, O rescaled in TMEM (tcgen05.ld/st) when the running
 //               max moves; final O / l written to global memory.
 // S_{j+1} is issued before P_j V_j, so the tensor pipe computes the next scores while the softmax warps work on the current tile.
@@ -22,9 +22,13 @@ namespace slam {
 constexpr int FA_BM = 128;   // query rows per CTA
 constexpr int FA_BN = 128;   // keys per tile
 constexpr int FA_DH = 64;
-constexpr int FA_THREADS = 256;
+constexpr int FA_THREADS = 192;                       // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: softmax (one per TMEM lane quarter)
 constexpr int FA_TILE_BYTES = 128 * 64 * 2;          // one 128 x 64 bf16 tile (Q, K_j, V_j, half of P_j)
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 + 2 + 4) + 256 + 1024;
+constexpr int FA_KST = 2;                            // K ring stages
+// Q + K ring + one V stage + one P buffer = 96 KB: TWO CTAs per SM, so one CTA's softmax (MUFU-bound) overlaps the other's
+// waits; each CTA allocates 256 TMEM columns (128 score + 64 output used)
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + FA_KST + 1 + 2) + 256 + 1024;
+constexpr float FA_RESCALE_TH = 8.0f;                // lazy rescale: keep a stale max while it is within 2^8 of the true one
 
 struct FmhaParams {
   int sq, sk, hq;
@@ -65,27 +69,26 @@ __host__ __device__ constexpr uint32_t fa_idesc(uint32_t M, uint32_t N, uint32_t
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, 2)
 fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + FA_TILE_BYTES;                  // 2 stages
-  uint8_t* sV = sK + 2 * FA_TILE_BYTES;              // 2 stages
-  uint8_t* sP = sV + 2 * FA_TILE_BYTES;              // 2 buffers x 2 K-blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * FA_TILE_BYTES);
+  uint8_t* sK = sQ + FA_TILE_BYTES;                  // FA_KST stages
+  uint8_t* sV = sK + FA_KST * FA_TILE_BYTES;         // 1 stage
+  uint8_t* sP = sV + FA_TILE_BYTES;                  // 1 buffer = 2 K-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_TILE_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* s_empty = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;   // [2]
-  uint64_t* pv_done = bars + 15;  // [2]  P buffer free again / O stable after P_j V_j
-  uint64_t* o_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 1;    // [FA_KST]
+  uint64_t* k_empty = bars + 3;   // [FA_KST]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;  // P buffer free again / O stable after P_j V_j
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -96,31 +99,28 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FA_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
-      mbar_init(&p_full[s], 4);
-      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(o_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;           // output accumulator: columns [256, 320)
+  const uint32_t tmem_base = *tmem_slot;             // score tile: columns [0, 128)
+  const uint32_t tmem_o = tmem_base + 128;           // output accumulator: columns [128, 192)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -129,17 +129,16 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sQ, &tmQ, q_full, h * FA_DH, b * p.sq + q0);
     }
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1u;
-      mbar_wait(&k_empty[st], ph ^ 1u);
+      const int ks = j % FA_KST;
+      mbar_wait(&k_empty[ks], ((j / FA_KST) & 1u) ^ 1u);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&k_full[st], FA_TILE_BYTES);
-        tma_load_2d(sK + st * FA_TILE_BYTES, &tmK, &k_full[st], h * FA_DH, b * p.sk + j * FA_BN);
+        mbar_arrive_expect_tx(&k_full[ks], FA_TILE_BYTES);
+        tma_load_2d(sK + ks * FA_TILE_BYTES, &tmK, &k_full[ks], h * FA_DH, b * p.sk + j * FA_BN);
       }
-      mbar_wait(&v_empty[st], ph ^ 1u);
+      mbar_wait(v_empty, (j & 1u) ^ 1u);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&v_full[st], FA_TILE_BYTES);
-        tma_load_2d(sV + st * FA_TILE_BYTES, &tmV, &v_full[st], h * FA_DH, b * p.sk + j * FA_BN);
+        mbar_arrive_expect_tx(v_full, FA_TILE_BYTES);
+        tma_load_2d(sV, &tmV, v_full, h * FA_DH, b * p.sk + j * FA_BN);
       }
       __syncwarp();
     }
@@ -148,59 +147,53 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_s = fa_idesc(128, FA_BN, 0);      // S = Q K^T : both operands K-major
     constexpr uint32_t idesc_o = fa_idesc(128, FA_DH, 1);      // O += P V  : V is MN-major
     auto issue_s = [&](int j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1u;
-      mbar_wait(&k_full[st], ph);
-      mbar_wait(&s_empty[st], ph ^ 1u);
+      const int ks = j % FA_KST;
+      mbar_wait(&k_full[ks], (j / FA_KST) & 1u);
+      mbar_wait(s_empty, (j & 1u) ^ 1u);                       // softmax of tile j-1 has the scores in registers
       tc_fence_after();
       if (lane == 0) {
         const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sQ));
-        const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + st * FA_TILE_BYTES));
+        const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + ks * FA_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < FA_DH / 16; ++k) umma_bf16(tmem_base + st * FA_BN, a_desc + 2u * k, b_desc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[st]);
+        for (int k = 0; k < FA_DH / 16; ++k) umma_bf16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(s_full);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_s(0);
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1u;
-      if (j + 1 < n_tiles) issue_s(j + 1);
-      mbar_wait(&p_full[st], ph);
-      mbar_wait(&v_full[st], ph);
+      if (j + 1 < n_tiles) issue_s(j + 1);                     // next scores overlap this tile's softmax
+      mbar_wait(p_full, j & 1u);
+      mbar_wait(v_full, j & 1u);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV + st * FA_TILE_BYTES));
+        const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
           // A = P: K-block k/4 (16 KB apart), 32 B per k-step inside it; B = V: 16 keys = two 8-row groups = 2048 B per k-step
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sP + (st * 2 + (k >> 2)) * FA_TILE_BYTES)) + 2u * (k & 3);
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2u * (k & 3);
           umma_bf16(tmem_o, a_desc, v_desc + 128u * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(&pv_done[st]);
-        if (j == n_tiles - 1) umma_commit(o_full);
+        umma_commit(v_empty);
+        umma_commit(pv_done);
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
-    const int qd = warp - 4;
+    const int qd = warp & 3;                                   // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    float m_run = -CUDART_INF_F, l_run = 0.0f;     // running max in the scaled log2 domain
+    float m_used = -CUDART_INF_F, l_run = 0.0f;                // exponent offset in use (scaled log2 domain), running sum
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1u;
       const int n0 = j * FA_BN;
-      mbar_wait(&s_full[st], ph);
+      mbar_wait(s_full, j & 1u);
       tc_fence_after();
-      const uint32_t ts = tmem_base + st * FA_BN + lane_base;
+      const uint32_t ts = tmem_base + lane_base;
       // the whole 128-wide score row lives in registers: one TMEM round trip per tile, and the score buffer is handed back
-      // to the MMA warp before any math
+      // to the MMA warp (which then computes S_{j+1}) before any math
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32(ts, s0);
       tmem_ld_32x32(ts + 32, s1);
@@ -209,8 +202,8 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
-      if (n0 + FA_BN > p.sk) {                       // key tail: columns >= sk never contribute
+      if (lane == 0) mbar_arrive(s_empty);
+      if (n0 + FA_BN > p.sk) {                                 // key tail: columns >= sk never contribute
         const uint32_t ninf = __float_as_uint(-CUDART_INF_F);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -224,16 +217,25 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int e = 0; e < 32; ++e)
         mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float corr = ex2_approx(m_run - m_new);          // 0 on the first tile (m_run = -inf)
-      const bool moved = m_new > m_run;
-      m_run = m_new;
-      // the P buffer of this parity was last read by P_{j-2} V_{j-2}
-      if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1u);
-      // p = exp2(s * scale - m): one FFMA + one MUFU per element; bf16 P into the swizzled K-major shared tile
+      const float m_tile = mx * p.scale_log2;
+      // lazy rescale (as in FlashAttention-4): exponents are taken relative to m_used, which is only raised when the true
+      // maximum runs more than 2^8 ahead (p <= 256 stays exact enough in bf16 / fp32) or on the first tile
+      const bool need = m_tile > m_used + FA_RESCALE_TH;
+      const bool any_need = __any_sync(0xffffffffu, need) != 0;
+      float corr = 1.0f;
+      if (any_need) {
+        const float m_new = fmaxf(m_used, m_tile);
+        corr = ex2_approx(m_used - m_new);                     // 0 on the first tile (m_used = -inf)
+        m_used = m_new;
+      }
+      const float neg_m = -m_used;
+      // the single P buffer is free again once P_{j-1} V_{j-1} has completed (also makes O stable for the rescale)
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1u);
+        tc_fence_after();
+      }
       float rs = 0.0f;
-      uint8_t* prow = sP + st * 2 * FA_TILE_BYTES + row * 128;
-      const float neg_m = -m_new;
+      uint8_t* prow = sP + row * 128;
       auto emit = [&](const uint32_t (&sv)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
@@ -256,10 +258,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       emit(s2, 2);
       emit(s3, 3);
       l_run = l_run * corr + rs;
-      // rescale the running output when any row of this warp raised its maximum (needs P_{j-1} V_{j-1} complete)
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1u);
-        tc_fence_after();
+      if (j > 0 && any_need) {                                 // rare after the first tiles: rescale the running output in TMEM
 #pragma unroll 1
         for (int c = 0; c < FA_DH / 32; ++c) {
           uint32_t r[32];
@@ -274,10 +273,10 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();            // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[st]);
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16 -> global
-    mbar_wait(o_full, 0);
+    mbar_wait(pv_done, (n_tiles - 1) & 1u);
     tc_fence_after();
     const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
     const int grow = q0 + row;
@@ -304,7 +303,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 typedef CUresult (*PFN_encodeTiledF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
