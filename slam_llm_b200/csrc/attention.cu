@@ -86,6 +86,7 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long 
 // (the fp32 output tile alone is 64 registers per 16 rows).
 template <int DH, int MT>
 __global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_kernel(const AttnP p) {
+  pdl_trigger();
   constexpr int BM = 64 * MT, BN = 64, PITCH = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_k
 // ------------------------------------------------------------------------------------------- backward
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 __global__ void attn_delta_kernel(const AttnP p, int dh) {
+  pdl_trigger();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int total = p.batch * p.sq * p.hq;
@@ -297,6 +299,7 @@ __global__ void attn_delta_kernel(const AttnP p, int dh) {
 // dQ partials go through fp32 atomics into dq_accum (as FlashAttention-2 does).
 template <int DH, int BQ>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
+  pdl_trigger();
   constexpr int BN = 64, PITCH = DH + 8, SPITCH = BQ + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sK = reinterpret_cast<bf16*>(smem_attn);
@@ -504,6 +507,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
 // dK/dV partials [2][rows][Hq][dh] (bf16) -> sum over the G heads of each KV group -> dk/dv [rows][Hkv][dh] with row strides
 __global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __restrict__ dk, long long lddk, bf16* __restrict__ dv, long long lddv,
                                       long long rows, int hq, int hkv, int dh) {
+  pdl_trigger();
   const int g = hq / hkv;
   const int vec_per_row = hkv * dh / 8;
   const long long total = 2 * rows * vec_per_row;
@@ -531,6 +535,7 @@ __global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __res
 
 // dq_accum f32 [B,Sq,Hq,DH] -> dq bf16 with row stride lddq
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq, long long rows, int width) {
+  pdl_trigger();
   const int vpr = width / 4;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = rows * vpr;

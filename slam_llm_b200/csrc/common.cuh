@@ -170,6 +170,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library lets its dependents start as early as possible (pdl_trigger); kernels launched with the
+// programmatic-stream-serialization attribute (the GEMMs) run their prologue (barrier init, TMEM alloc, descriptor prefetch)
+// under the tail of the previous kernel and call pdl_wait() before touching memory it produced.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -38,6 +38,7 @@ __device__ __forceinline__ float block_sum(float v, float* sbuf) {
 
 // ---------------------------------------------------------------- casts / adds
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n, float scale) {
+  pdl_trigger();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -82,6 +83,7 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
   }
 }
 __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ yv, bf16* __restrict__ dx, int64_t n) {
+  pdl_trigger();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -108,6 +110,7 @@ static inline int ew_grid(int64_t n, int per_thread, int threads) {
 
 // ---------------------------------------------------------------- transpose (bf16, 64x64 tiles via smem)
 __global__ void transpose_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy, int rows, int cols) {
+  pdl_trigger();
   __shared__ bf16 tile[64][66];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
@@ -143,6 +146,7 @@ __global__ void transpose_f32_batched_kernel(const float* __restrict__ src, floa
 
 // ---------------------------------------------------------------- row gather / scatter (d % 8 == 0)
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ idx, bf16* __restrict__ y, int n_idx, int d, int scatter) {
+  pdl_trigger();
   const int i = blockIdx.x;
   if (i >= n_idx) return;
   const int64_t src = scatter ? i : idx[i];
@@ -183,6 +187,7 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
 template <int VPT>  // 8-element vectors per thread held in registers
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                           float* __restrict__ rstd_out, int d, float eps) {
+  pdl_trigger();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * d);
@@ -220,6 +225,7 @@ template <int VPT>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                           const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                           bf16* __restrict__ dx, int d) {
+  pdl_trigger();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const int nvec = d / 8;
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
 template <int VPT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                         bf16* __restrict__ y, int d, float eps) {
+  pdl_trigger();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * d);
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 // x viewed as [rows, n_heads, dh] with row stride ld; cos/sin f32 [seq_len, dh/2]; 8 pairs per thread
 __global__ void rope_kernel(bf16* __restrict__ x, int64_t ld, int rows, int seq_len, int n_heads, int dh, const float* __restrict__ cosT,
                             const float* __restrict__ sinT, int inverse) {
+  pdl_trigger();
   const int half = dh / 2;
   const int vec_per_head = half / 8;
   const int64_t total = static_cast<int64_t>(rows) * n_heads * vec_per_head;
@@ -351,6 +359,7 @@ __global__ void rope_kernel(bf16* __restrict__ x, int64_t ld, int rows, int seq_
 
 // ---------------------------------------------------------------- SwiGLU (HF LlamaMLP; modeling_llama.py:182-184)
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, int rows, int f) {
+  pdl_trigger();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -367,6 +376,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   }
 }
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dh, bf16* __restrict__ dgu, int rows, int f) {
+  pdl_trigger();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -420,6 +430,7 @@ __device__ __forceinline__ void mask_span(const uint8_t* __restrict__ mrow, int 
 
 __global__ void embed_merge_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, const bf16* __restrict__ audio, int ta,
                                    const bf16* __restrict__ embed, bf16* __restrict__ x, int s, int d) {
+  pdl_trigger();
   __shared__ int sh[2];
   const int b = blockIdx.y, r = blockIdx.x;
   const uint8_t* mrow = mask + static_cast<int64_t>(b) * s;
@@ -460,6 +471,7 @@ __global__ void embed_merge_bwd_kernel(const uint8_t* __restrict__ mask, const b
 // col[b, t, kk*C + c] = x[b, stride*t + kk - 1, c]; one block per output row; zero fill outside and for cols >= 3C
 template <typename TIn>
 __global__ void im2col_kernel(const TIn* __restrict__ x, int t_in, int c, int stride, int t_out, bf16* __restrict__ col, int64_t ldk) {
+  pdl_trigger();
   const int b = blockIdx.y, t = blockIdx.x;
   bf16* out = col + (static_cast<int64_t>(b) * t_out + t) * ldk;
   for (int j = threadIdx.x; j < ldk; j += blockDim.x) {
@@ -476,6 +488,7 @@ __global__ void im2col_kernel(const TIn* __restrict__ x, int t_in, int c, int st
   }
 }
 __global__ void add_pos_kernel(bf16* __restrict__ x, const float* __restrict__ pos, int t, int d, int64_t total_vec) {
+  pdl_trigger();
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int vpr = d / 8;
@@ -503,6 +516,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
 }
 // y = x * keep / (1 - p)
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n, uint32_t thresh, float inv_keep, uint64_t seed) {
+  pdl_trigger();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -516,6 +530,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 // out = base + lora * keep / (1 - p)   (dX of a LoRA linear under dropout: dY W + mask o ((dY sB) A))
 __global__ void dropout_bwd_add_kernel(const bf16* __restrict__ base, const bf16* __restrict__ lora, bf16* __restrict__ out, int64_t n, uint32_t thresh,
                                        float inv_keep, uint64_t seed) {
+  pdl_trigger();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {

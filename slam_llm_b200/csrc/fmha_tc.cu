@@ -72,6 +72,7 @@ __host__ __device__ constexpr uint32_t fa_idesc(uint32_t M, uint32_t N, uint32_t
 __global__ void __launch_bounds__(FA_THREADS, 2)
 fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const FmhaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;

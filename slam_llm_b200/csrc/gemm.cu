@@ -118,6 +118,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // dependents may begin their own prologue now ...
+  pdl_wait();      // ... and this grid must not read its operands before the producing grid has completed
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // work items
   const int nkb = p.kb1 + p.kb2;
@@ -393,7 +395,21 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   p.ksplit = static_cast<int>(ceil_div(nkb_total, p.kb_per_split));   // no empty k-slices
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<BLOCK_M, BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_M, BLOCK_N>, tmA, tmB, tmA2, tmB2, p);
+  if (le != cudaSuccess) {
+    set_error("slam_gemm_bf16: cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return static_cast<int>(le);
+  }
   SLAM_LAUNCH_CHECK("slam_gemm_bf16");
   return 0;
 }
@@ -408,8 +424,11 @@ static int pick_tile(int m, int n, int k) {
   if (n <= 64) return 128 * 1000 + 64;
   if (n < 192) return 128 * 1000 + 128;
   const int sms = num_sms();
-  const int64_t t256 = ceil_div(m, 256) * ceil_div(n, 256);
-  if (k >= 5000 && n >= 256 && t256 <= sms && t256 * 10 >= sms * 6) return 256 * 1000 + 256;   // one well-filled wave
+  if (k >= 5000 && n >= 256) {   // one well-filled wave of 256-row tiles: prefer the width that uses the most SMs
+    const int64_t t224 = ceil_div(m, 256) * ceil_div(n, 224), t256 = ceil_div(m, 256) * ceil_div(n, 256);
+    if (t224 <= sms && t224 > t256 && t224 * 10 >= sms * 6) return 256 * 1000 + 224;
+    if (t256 <= sms && t256 * 10 >= sms * 6) return 256 * 1000 + 256;
+  }
   const int64_t mt = ceil_div(m, 128);
   const int cands[3] = {256, 192, 128};
   const double pen[3] = {1.0, 1.04, 1.5};
@@ -451,6 +470,7 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
     case 128128: return launch_gemm<128, 128>(g, st);
     case 128064: return launch_gemm<128, 64>(g, st);
     case 256256: return launch_gemm<256, 256>(g, st);
+    case 256224: return launch_gemm<256, 224>(g, st);
     case 256192: return launch_gemm<256, 192>(g, st);
     case 256128: return launch_gemm<256, 128>(g, st);
     default: set_error("gemm: unsupported tile %d", tile); return -1;

