@@ -1,5 +1,6 @@
-// tcgen05 / TMEM flash-attention forward for the Whisper encoder (dh = 64, non-causal, no mask) — the sm_100a replacement of the
-// mma.sync kernel in attention.cu for that shape (whisper qkv_attention via models/encoder.py:26-27).
+// tcgen05 / TMEM flash-attention forward: the Whisper encoder shape (dh = 64, non-causal, unmasked; whisper qkv_attention via
+// models/encoder.py:26-27) and the Llama decoder shape (dh = 64/128, causal + key-padding mask, GQA, lse
+// for the backward; HF LlamaAttention).  The mma.sync kernel in attention.cu remains for other shapes.
 //
 // One CTA = 128 query rows of one (batch, head); the key/value sequence is walked in tiles of 128 keys.
 //   warp 0      TMA producer: Q tile once, then K (2-stage ring) and V tiles (128 x 64 bf16, 128B swizzle)
@@ -21,20 +22,28 @@ namespace slam {
 
 constexpr int FA_BM = 128;   // query rows per CTA
 constexpr int FA_BN = 128;   // keys per tile
-constexpr int FA_DH = 64;
-constexpr int FA_THREADS = 192;                       // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: softmax (one per TMEM lane quarter)
-constexpr int FA_TILE_BYTES = 128 * 64 * 2;          // one 128 x 64 bf16 tile (Q, K_j, V_j, half of P_j)
+constexpr int FA_THREADS = 192;                       // warp 0: TMA (+ key-mask bits), warp 1: TMEM alloc + MMA, warps 2-5: softmax
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;          // one 128 x 64 bf16 block (dh = 128 tiles are two such blocks)
 constexpr int FA_KST = 2;                            // K ring stages
-// Q + K ring + one V stage + one P buffer = 96 KB: TWO CTAs per SM, so one CTA's softmax (MUFU-bound) overlaps the other's
-// waits; each CTA allocates 256 TMEM columns (128 score + 64 output used)
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + FA_KST + 1 + 2) + 256 + 1024;
 constexpr float FA_RESCALE_TH = 8.0f;                // lazy rescale: keep a stale max while it is within 2^8 of the true one
 
+template <int DH>
+struct FaCfg {
+  static constexpr int NB = DH / 64;                 // 64-wide blocks per head vector
+  // dh = 64: Q + K ring + V + P = 96 KB -> TWO CTAs per SM (one CTA's MUFU-bound softmax overlaps the other's waits);
+  // dh = 128: 160 KB, one CTA per SM.  TMEM: 128 score columns + DH output columns (256 allocated).
+  static constexpr int SMEM = FA_TILE_BYTES * (NB * (1 + FA_KST + 1) + 2) + 512 + 1024;
+  static constexpr int CTAS_PER_SM = DH == 64 ? 2 : 1;
+};
+
 struct FmhaParams {
-  int sq, sk, hq;
+  int sq, sk, hq, hkv;
+  int causal;
   float scale_log2;
   bf16* out;
   long long ldo;
+  float* lse;                 // [B, Hq, Sq] natural-log lse, or NULL
+  const uint8_t* key_mask;    // [B, Sk] (1 = attend) or NULL
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -58,7 +67,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;              // LBO: distance between 64-element MN blocks (single block here)
+  d |= static_cast<uint64_t>(1) << 16;              // LBO: distance between 64-element MN blocks (single block per MMA here)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;      // SBO: distance between 8-row K groups
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
@@ -69,16 +78,18 @@ __host__ __device__ constexpr uint32_t fa_idesc(uint32_t M, uint32_t N, uint32_t
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+// MASKED = causal and/or key-padding mask and/or lse output (the Llama decoder); otherwise the Whisper encoder shape.
+template <int DH, bool MASKED>
+__global__ void __launch_bounds__(FA_THREADS, FaCfg<DH>::CTAS_PER_SM)
 fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const FmhaParams p) {
-  pdl_trigger();
+  constexpr int NB = FaCfg<DH>::NB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + FA_TILE_BYTES;                  // FA_KST stages
-  uint8_t* sV = sK + FA_KST * FA_TILE_BYTES;         // 1 stage
-  uint8_t* sP = sV + FA_TILE_BYTES;                  // 1 buffer = 2 K-blocks
+  uint8_t* sQ = smem;                                 // NB blocks
+  uint8_t* sK = sQ + NB * FA_TILE_BYTES;              // FA_KST stages x NB blocks
+  uint8_t* sV = sK + FA_KST * NB * FA_TILE_BYTES;     // NB blocks (block nb = head dims [64 nb, 64 nb + 64))
+  uint8_t* sP = sV + NB * FA_TILE_BYTES;              // 2 K-blocks of 64 keys
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [FA_KST]
@@ -89,13 +100,19 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_empty = bars + 8;
   uint64_t* p_full = bars + 9;
   uint64_t* pv_done = bars + 10;  // P buffer free again / O stable after P_j V_j
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* m_full = bars + 11;   // [FA_KST] key-mask bits of the tile are in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* s_maskbits = tmem_slot + 4;               // [FA_KST][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.hq / p.hkv);
   const int q0 = blockIdx.x * FA_BM;
-  const int n_tiles = (p.sk + FA_BN - 1) / FA_BN;
+  int n_tiles = (p.sk + FA_BN - 1) / FA_BN;
+  if (MASKED && p.causal) n_tiles = min(n_tiles, (q0 + FA_BM + FA_BN - 1) / FA_BN);   // tiles above the diagonal never contribute
+  const bool has_mask = MASKED && p.key_mask != nullptr;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -104,6 +121,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int s = 0; s < FA_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+      mbar_init(&m_full[s], 1);
     }
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
@@ -121,42 +139,64 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;             // score tile: columns [0, 128)
-  const uint32_t tmem_o = tmem_base + 128;           // output accumulator: columns [128, 192)
+  const uint32_t tmem_o = tmem_base + 128;           // output accumulator: columns [128, 128 + DH)
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (+ key-mask bits)
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, h * FA_DH, b * p.sq + q0);
+      mbar_arrive_expect_tx(q_full, NB * FA_TILE_BYTES);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) tma_load_2d(sQ + nb * FA_TILE_BYTES, &tmQ, q_full, h * DH + nb * 64, b * p.sq + q0);
     }
     for (int j = 0; j < n_tiles; ++j) {
       const int ks = j % FA_KST;
-      mbar_wait(&k_empty[ks], ((j / FA_KST) & 1u) ^ 1u);
+      mbar_wait(&k_empty[ks], ((j / FA_KST) & 1u) ^ 1u);     // (the softmax warps of tile j - FA_KST are long past their mask bits)
       if (lane == 0) {
-        mbar_arrive_expect_tx(&k_full[ks], FA_TILE_BYTES);
-        tma_load_2d(sK + ks * FA_TILE_BYTES, &tmK, &k_full[ks], h * FA_DH, b * p.sk + j * FA_BN);
+        mbar_arrive_expect_tx(&k_full[ks], NB * FA_TILE_BYTES);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+          tma_load_2d(sK + (ks * NB + nb) * FA_TILE_BYTES, &tmK, &k_full[ks], hk * DH + nb * 64, b * p.sk + j * FA_BN);
+      }
+      if (has_mask) {
+        // 128 key-mask bytes of this tile -> 4 words of bits (lane l covers keys 4l .. 4l+3)
+        uint32_t nib = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j * FA_BN + 4 * lane + e;
+          if (col < p.sk && p.key_mask[static_cast<long long>(b) * p.sk + col] != 0) nib |= 1u << e;
+        }
+        uint32_t v = nib << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        if ((lane & 7) == 0) s_maskbits[ks * 4 + (lane >> 3)] = v;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&m_full[ks]);
       }
       mbar_wait(v_empty, (j & 1u) ^ 1u);
       if (lane == 0) {
-        mbar_arrive_expect_tx(v_full, FA_TILE_BYTES);
-        tma_load_2d(sV, &tmV, v_full, h * FA_DH, b * p.sk + j * FA_BN);
+        mbar_arrive_expect_tx(v_full, NB * FA_TILE_BYTES);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) tma_load_2d(sV + nb * FA_TILE_BYTES, &tmV, v_full, hk * DH + nb * 64, b * p.sk + j * FA_BN);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = fa_idesc(128, FA_BN, 0);      // S = Q K^T : both operands K-major
-    constexpr uint32_t idesc_o = fa_idesc(128, FA_DH, 1);      // O += P V  : V is MN-major
+    constexpr uint32_t idesc_o = fa_idesc(128, 64, 1);         // O[:, 64 nb ..] += P V[:, 64 nb ..] : V is MN-major
     auto issue_s = [&](int j) {
       const int ks = j % FA_KST;
       mbar_wait(&k_full[ks], (j / FA_KST) & 1u);
       mbar_wait(s_empty, (j & 1u) ^ 1u);                       // softmax of tile j-1 has the scores in registers
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sQ));
-        const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + ks * FA_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < FA_DH / 16; ++k) umma_bf16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sQ + (k >> 2) * FA_TILE_BYTES)) + 2u * (k & 3);
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + (ks * NB + (k >> 2)) * FA_TILE_BYTES)) + 2u * (k & 3);
+          umma_bf16(tmem_base, a_desc, b_desc, idesc_s, k > 0 ? 1u : 0u);
+        }
         umma_commit(&k_empty[ks]);
         umma_commit(s_full);
       }
@@ -170,12 +210,14 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(v_full, j & 1u);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
-          // A = P: K-block k/4 (16 KB apart), 32 B per k-step inside it; B = V: 16 keys = two 8-row groups = 2048 B per k-step
+          // A = P: K-block k/4 (16 KB apart), 32 B per k-step inside it; B = V block nb: 16 keys = two 8-row groups = 2048 B per k-step
           const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2u * (k & 3);
-          umma_bf16(tmem_o, a_desc, v_desc + 128u * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+            umma_bf16(tmem_o + nb * 64, a_desc, make_sw128_mnmajor_desc(smem_u32(sV + nb * FA_TILE_BYTES)) + 128u * k, idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(v_empty);
         umma_commit(pv_done);
@@ -186,6 +228,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
     const int qd = warp & 3;                                   // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
+    const int grow = q0 + row;
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
     float m_used = -CUDART_INF_F, l_run = 0.0f;                // exponent offset in use (scaled log2 domain), running sum
     for (int j = 0; j < n_tiles; ++j) {
@@ -204,8 +247,8 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
+      const uint32_t ninf = __float_as_uint(-CUDART_INF_F);
       if (n0 + FA_BN > p.sk) {                                 // key tail: columns >= sk never contribute
-        const uint32_t ninf = __float_as_uint(-CUDART_INF_F);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           if (n0 + e >= p.sk) s0[e] = ninf;
@@ -214,22 +257,47 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (n0 + 96 + e >= p.sk) s3[e] = ninf;
         }
       }
+      if (MASKED) {
+        if (p.causal && n0 + FA_BN - 1 > q0) {                 // diagonal tile: keys after the query are masked
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (n0 + e > grow) s0[e] = ninf;
+            if (n0 + 32 + e > grow) s1[e] = ninf;
+            if (n0 + 64 + e > grow) s2[e] = ninf;
+            if (n0 + 96 + e > grow) s3[e] = ninf;
+          }
+        }
+        if (has_mask) {
+          const int ks = j % FA_KST;
+          mbar_wait(&m_full[ks], (j / FA_KST) & 1u);
+          const uint32_t b0 = s_maskbits[ks * 4], b1 = s_maskbits[ks * 4 + 1], b2 = s_maskbits[ks * 4 + 2], b3 = s_maskbits[ks * 4 + 3];
+          if ((b0 & b1 & b2 & b3) != 0xffffffffu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (!((b0 >> e) & 1u)) s0[e] = ninf;
+              if (!((b1 >> e) & 1u)) s1[e] = ninf;
+              if (!((b2 >> e) & 1u)) s2[e] = ninf;
+              if (!((b3 >> e) & 1u)) s3[e] = ninf;
+            }
+          }
+        }
+      }
       float mx = -CUDART_INF_F;
 #pragma unroll
       for (int e = 0; e < 32; ++e)
         mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
       const float m_tile = mx * p.scale_log2;
       // lazy rescale (as in FlashAttention-4): exponents are taken relative to m_used, which is only raised when the true
-      // maximum runs more than 2^8 ahead (p <= 256 stays exact enough in bf16 / fp32) or on the first tile
+      // maximum runs more than 2^8 ahead (p <= 256 stays exact enough in bf16 / fp32) or on the first unmasked tile
       const bool need = m_tile > m_used + FA_RESCALE_TH;
       const bool any_need = __any_sync(0xffffffffu, need) != 0;
       float corr = 1.0f;
       if (any_need) {
         const float m_new = fmaxf(m_used, m_tile);
-        corr = ex2_approx(m_used - m_new);                     // 0 on the first tile (m_used = -inf)
+        corr = m_new == -CUDART_INF_F ? 1.0f : ex2_approx(m_used - m_new);   // 0 when the row sees its first unmasked key
         m_used = m_new;
       }
-      const float neg_m = -m_used;
+      const float neg_m = m_used == -CUDART_INF_F ? 0.0f : -m_used;          // fully masked so far: exp2(-inf - 0) = 0
       // the single P buffer is free again once P_{j-1} V_{j-1} has completed (also makes O stable for the rescale)
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1u);
@@ -261,7 +329,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       l_run = l_run * corr + rs;
       if (j > 0 && any_need) {                                 // rare after the first tiles: rescale the running output in TMEM
 #pragma unroll 1
-        for (int c = 0; c < FA_DH / 32; ++c) {
+        for (int c = 0; c < DH / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_o + lane_base + c * 32, r);
           tmem_ld_wait();
@@ -276,18 +344,19 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l -> bf16 -> global
+    // epilogue: O / l -> bf16 -> global (+ lse)
     mbar_wait(pv_done, (n_tiles - 1) & 1u);
     tc_fence_after();
     const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-    const int grow = q0 + row;
+    if (MASKED && p.lse != nullptr && grow < p.sq)
+      p.lse[(static_cast<long long>(b) * p.hq + h) * p.sq + grow] = l_run > 0.0f ? m_used * 0.6931471805599453f + logf(l_run) : 0.0f;
 #pragma unroll 1
-    for (int c = 0; c < FA_DH / 32; ++c) {
+    for (int c = 0; c < DH / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_o + lane_base + c * 32, r);
       tmem_ld_wait();
       if (grow < p.sq) {
-        bf16* o = p.out + (static_cast<long long>(b) * p.sq + grow) * p.ldo + h * FA_DH + c * 32;
+        bf16* o = p.out + (static_cast<long long>(b) * p.sq + grow) * p.ldo + h * DH + c * 32;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           uint4 pk;
@@ -334,36 +403,47 @@ static int fa_make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long l
   return 0;
 }
 
-// Returns 1 if the shape is not handled by the tcgen05 kernel (caller falls through to the mma.sync kernel), 0 on success.
-int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
-  if (a->dh != 64 || a->causal || a->key_mask != nullptr || a->lse != nullptr || a->hq != a->hkv || a->sq != a->sk || a->sk < 128) return 1;
-  if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->k) & 15) || (reinterpret_cast<uintptr_t>(a->v) & 15)) return 1;
+template <int DH, bool MASKED>
+static int fa_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FmhaParams& p, dim3 grid, cudaStream_t st) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_tc_kernel<DH, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaCfg<DH>::SMEM);
     if (e != cudaSuccess) {
       set_error("fmha: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
     }
     set = true;
   }
+  fmha_fwd_tc_kernel<DH, MASKED><<<grid, FA_THREADS, FaCfg<DH>::SMEM, st>>>(tq, tk, tv, p);
+  SLAM_LAUNCH_CHECK("slam_attn_fwd.tcgen05");
+  return 0;
+}
+
+// Returns 1 if the shape is not handled by the tcgen05 kernels (caller falls through to the mma.sync kernel), 0 on success.
+int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
+  if ((a->dh != 64 && a->dh != 128) || a->sq != a->sk || a->sk < 64 || a->hkv <= 0 || a->hq % a->hkv != 0) return 1;
+  if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->k) & 15) || (reinterpret_cast<uintptr_t>(a->v) & 15)) return 1;
   CUtensorMap tq, tk, tv;
   const long long rows_q = static_cast<long long>(a->batch) * a->sq, rows_k = static_cast<long long>(a->batch) * a->sk;
   int rc;
-  if ((rc = fa_make_tmap(&tq, a->q, rows_q, static_cast<long long>(a->hq) * 64, a->ldq)) != 0) return rc;
-  if ((rc = fa_make_tmap(&tk, a->k, rows_k, static_cast<long long>(a->hkv) * 64, a->ldk)) != 0) return rc;
-  if ((rc = fa_make_tmap(&tv, a->v, rows_k, static_cast<long long>(a->hkv) * 64, a->ldv)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tq, a->q, rows_q, static_cast<long long>(a->hq) * a->dh, a->ldq)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tk, a->k, rows_k, static_cast<long long>(a->hkv) * a->dh, a->ldk)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tv, a->v, rows_k, static_cast<long long>(a->hkv) * a->dh, a->ldv)) != 0) return rc;
   FmhaParams p;
   p.sq = a->sq;
   p.sk = a->sk;
   p.hq = a->hq;
+  p.hkv = a->hkv;
+  p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.ldo = a->ldo;
+  p.lse = a->lse;
+  p.key_mask = a->key_mask;
   dim3 grid(static_cast<unsigned>(ceil_div(a->sq, FA_BM)), a->hq, a->batch);
-  fmha_fwd_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, p);
-  SLAM_LAUNCH_CHECK("slam_attn_fwd.tcgen05");
-  return 0;
+  const bool masked = a->causal || a->key_mask != nullptr || a->lse != nullptr;
+  if (a->dh == 64) return masked ? fa_launch<64, true>(tq, tk, tv, p, grid, st) : fa_launch<64, false>(tq, tk, tv, p, grid, st);
+  return masked ? fa_launch<128, true>(tq, tk, tv, p, grid, st) : fa_launch<128, false>(tq, tk, tv, p, grid, st);
 }
 
 }  // namespace slam

@@ -243,6 +243,10 @@ def _ref_attn(q, k, v, causal, scale, key_mask):
     (2, 400, 32, 8, 128, True, True),      # Llama-3-8B decoder, GQA 4:1
     (2, 150, 32, 4, 64, True, True),       # TinyLlama decoder, GQA 8:1
     (1, 65, 4, 4, 128, True, False),
+    (4, 401, 32, 8, 128, True, True),      # BASELINE config 3 decoder shape (tcgen05 kernel, dh = 128)
+    (1, 700, 8, 8, 128, True, False),      # several key tiles, causal tile skipping
+    (2, 200, 4, 4, 64, False, True),       # key mask without causal
+    (1, 40, 4, 2, 64, True, True),         # short: mma.sync kernel
 ])
 def test_attention_fwd_bwd(ops, B, S, Hq, Hkv, dh, causal, masked):
     qkv = rnd(B * S, (Hq + 2 * Hkv) * dh, seed=27)  # fused QKV buffer, used in place
@@ -261,6 +265,16 @@ def test_attention_fwd_bwd(ops, B, S, Hq, Hkv, dh, causal, masked):
     valid = torch.ones(B, S, dtype=torch.bool, device=dev()) if key_mask is None else key_mask.bool()
     sel = valid[:, :, None, None].expand_as(ref)
     assert rel_err(out[sel], ref[sel]) < 1.5e-2, rel_err(out[sel], ref[sel])
+    # lse [B, Hq, S] (natural log) against the fp32 logsumexp of the masked scores, on rows that see at least one key
+    sc = (qr.detach().transpose(1, 2) @ kr.detach().transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1).transpose(-1, -2)) * scale
+    m = torch.ones(B, 1, S, S, dtype=torch.bool, device=dev())
+    if causal:
+        m = m & torch.ones(S, S, dtype=torch.bool, device=dev()).tril()
+    if key_mask is not None:
+        m = m & key_mask.bool()[:, None, None, :]
+    lse_ref = torch.logsumexp(sc.masked_fill(~m, float("-inf")), dim=-1)
+    ok = torch.isfinite(lse_ref)
+    assert (lse[ok] - lse_ref[ok]).abs().max().item() < 2e-2, (lse[ok] - lse_ref[ok]).abs().max().item()
     if not causal:
         return
     dout = rnd(B, S, Hq, dh, seed=28) * valid[:, :, None, None].to(BF16)  # padded query rows get zero grad
