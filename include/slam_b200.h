@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SLAM_B200_ABI_VERSION 1
+#define SLAM_B200_ABI_VERSION 2
 
 int slam_abi_version(void);
 const char* slam_last_error(void);
@@ -55,12 +55,24 @@ typedef struct slam_gemm_args {
   float alpha;
   int32_t m, n;
   int32_t block_n;                /* tile override: 0 = auto; 64/128/192/256 = BLOCK_N with 128-row tiles;
-                                     BLOCK_M*1000+BLOCK_N (e.g. 256256) = explicit 256-row tile */
+                                     BLOCK_M*1000+BLOCK_N (e.g. 256256) = explicit 256-row tile;
+                                     2000000+BLOCK_N (256/224/192/160/128) = CTA-pair kernel (cta_group::2: 256 x BLOCK_N per SM pair) */
   int32_t split_k;                /* <= 1: off.  > 1: K is cut into that many slices processed by different CTAs and merged with
                                      fp32 atomics into `out`, which must be f32 and ZERO-INITIALISED by the caller; no bias /
                                      activation / residual (thin LoRA products, lm_head dgrad: few output tiles, long K) */
+  void* workspace;                /* NULL, or slam_gemm_workspace_bytes() bytes of device memory, ZEROED ONCE by the caller and then
+                                     owned by the library between calls on one stream (it leaves the flag area zeroed).  With a
+                                     workspace the GEMM may "split the tail": the tiles of the last, partial wave are cut into
+                                     k-slices run by otherwise idle SMs; the fp32 partial accumulators are exchanged through the
+                                     workspace and added in a fixed order (deterministic), and the full epilogue (bias /
+                                     activation / residual, bf16 or f32 out) still applies */
+  int64_t workspace_bytes;
+  int32_t tail_split;             /* 0 = automatic (when a workspace is given), -1 = never, n > 1 = at most n k-slices per tile */
+  int32_t reserved;
 } slam_gemm_args;
 int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
+/* bytes of `workspace` the tail split needs on the current device (SM count x one 128 x 256 fp32 tile + flags) */
+int64_t slam_gemm_workspace_bytes(void);
 
 /* C[P,Q] (f32) = scale * sum_m A[m,P] * B[m,Q]   (thin weight-gradient product: P <= 64)
  * Used for LoRA dA / dB (peft lora.Linear backward) and bias gradients.  C is OVERWRITTEN. */

@@ -170,6 +170,157 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- warp-uniform issue helpers
+// The MMA-issuing warp of the GEMM kernels is instruction-bound, not data-bound (ncu source page, round 1: ~90 SASS
+// instructions and ~830 cycles per 64-wide k-block when the four tcgen05.mma were issued from an `if (lane == 0)` branch -
+// the compiler wraps every asm in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop).  These helpers are executed by the
+// WHOLE warp with warp-uniform operands; the election happens inside the asm, so the operands live in uniform registers and
+// the four UTCHMMA of a k-block issue back to back.
+constexpr uint32_t SW128_KMAJOR_DESC_HI = 0x40004040u;   // SBO = 1024 B, descriptor version 1, SWIZZLE_128B (bits 32..63)
+// low word of the K-major SW128 descriptor of a tile at shared address `addr` (LBO field = 1)
+__device__ __forceinline__ uint32_t sw128_kmajor_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+#define SLAM_UMMA_STEP(CG, DOFF, AOFF, BOFF, PRED)                                                   \
+  "add.u32 alo, %1, " #AOFF ";\n\t add.u32 blo, %2, " #BOFF ";\n\t add.u32 dd, %0, " #DOFF ";\n\t"   \
+  "mov.b64 da, {alo, %5};\n\t mov.b64 db, {blo, %5};\n\t"                                             \
+  "@lead tcgen05.mma.cta_group::" #CG ".kind::f16 [dd], da, db, %3, " PRED ";\n\t"
+
+// one 64-wide k-block (4 x K=16) into the accumulator at d_tmem; `accumulate` = 0 overwrites on the first step
+__device__ __forceinline__ void umma_kblock_1(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, lead;\n\t.reg .b64 da, db;\n\t.reg .b32 alo, blo, dd;\n\t"
+      "elect.sync _|lead, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      SLAM_UMMA_STEP(1, 0, 0, 0, "p") SLAM_UMMA_STEP(1, 0, 2, 2, "1") SLAM_UMMA_STEP(1, 0, 4, 4, "1") SLAM_UMMA_STEP(1, 0, 6, 6, "1")
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
+      : "memory");
+}
+// CTA-pair variant (cta_group::2, leader CTA only)
+__device__ __forceinline__ void umma_kblock_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, lead;\n\t.reg .b64 da, db;\n\t.reg .b32 alo, blo, dd;\n\t"
+      "elect.sync _|lead, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      SLAM_UMMA_STEP(2, 0, 0, 0, "p") SLAM_UMMA_STEP(2, 0, 2, 2, "1") SLAM_UMMA_STEP(2, 0, 4, 4, "1") SLAM_UMMA_STEP(2, 0, 6, 6, "1")
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
+      : "memory");
+}
+// one elected lane commits: mbarrier arrive once all previously issued tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred lead;\n\telect.sync _|lead, 0xffffffff;\n\t"
+      "@lead tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_addr)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred lead;\n\t.reg .b16 m;\n\telect.sync _|lead, 0xffffffff;\n\tmov.b16 m, 3;\n\t"
+      "@lead tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar_addr)
+      : "memory");
+}
+// TMA tile load issued by one elected lane of a converged warp (operands warp-uniform)
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "{\n\t.reg .pred lead;\n\telect.sync _|lead, 0xffffffff;\n\t"
+      "@lead cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "{\n\t.reg .pred lead;\n\telect.sync _|lead, 0xffffffff;\n\t"
+      "@lead cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred lead;\n\telect.sync _|lead, 0xffffffff;\n\t"
+      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar_addr), "r"(bytes)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): two SMs of one TPC run one M=256 MMA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier that CTAs of the whole cluster arrive on (acquire at cluster scope); same watchdog as mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+#if SLAM_WATCHDOG
+    if (++spins == 1024u) t0 = clock64();
+    if (spins > 1024u && (spins & 1023u) == 0u && clock64() - t0 > 4000000000LL) {
+      printf("slam_b200: cluster mbarrier watchdog block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+#endif
+  }
+  (void)t0;
+  (void)spins;
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier given as a shared::cluster
+// address (the pair leader's barrier): both CTAs of a pair feed one "stage full" barrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// TMEM management for a CTA pair: one warp (same warp index) of EACH CTA executes these
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N columns: N/2 from each CTA's smem]; leader CTA only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in every CTA of cta_mask once the issued pair MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // Every kernel of the library lets its dependents start as early as possible (pdl_trigger); kernels launched with the
 // programmatic-stream-serialization attribute (the GEMMs) run their prologue (barrier init, TMEM alloc, descriptor prefetch)

@@ -16,34 +16,21 @@
 // The K loop runs over TWO operand pairs back to back ("dual K segment"): the base weights and the
 // rank-padded LoRA pair, so y = xW^T + (alpha/r)(xA^T)B^T is produced in ONE accumulator tile
 // (reference: peft lora.Linear.forward called under models/slam_model.py:400).
+#include <atomic>
+#include <chrono>
 #include <mutex>
 
 #include "../../include/slam_b200.h"
 #include "common.cuh"
+#include "gemm_common.cuh"
+#include "gemm_2cta.cuh"
 #include "host.cuh"
 
 namespace slam {
 
-constexpr int GEMM_BK = 64;
 #ifndef SLAM_GEMM_PREFETCH
 #define SLAM_GEMM_PREFETCH 0   // L2 prefetch distance of the weight operand in k-blocks; measured on B200: 4/8/16 are ~10 % SLOWER than 0 (profiles/r01_exp_prefetch.log)
 #endif
-constexpr int GEMM_THREADS = 256;
-
-struct GemmKParams {
-  int M, N;
-  int kb1, kb2;
-  int ksplit, kb_per_split;   // split-K: work item = (tile, k-slice); partial tiles are merged with fp32 atomics
-  int num_m_tiles, num_n_tiles;
-  void* out;
-  long long ldo;
-  int out_f32;
-  int act;
-  const float* bias;
-  const bf16* residual;
-  long long ldr;
-  float alpha;
-};
 
 template <int BLOCK_M, int BLOCK_N>
 struct GemmCfg {
@@ -61,7 +48,7 @@ struct GemmCfg {
   static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_PITCH = 36;                                    // floats per staged row (32 + 4 pad: conflict-free)
+  static constexpr int EPI_PITCH = GEMM_EPI_PITCH;
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                 // one 32x32 fp32 chunk per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
@@ -85,7 +72,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xchg_bar = tempty_bar + 2;   // [4] tail-split exchange: one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xchg_bar + 4);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -108,6 +96,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&xchg_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -121,99 +110,76 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_trigger();   // dependents may begin their own prologue now ...
   pdl_wait();      // ... and this grid must not read its operands before the producing grid has completed
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // work items
-  const int nkb = p.kb1 + p.kb2;
-
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    // The B operand (weights) streams from HBM and every M-tile of an N-tile asks for the same B tile at the same time, so
-    // without help each load sees the full HBM latency and the mainloop is bound by bytes-in-flight / latency (measured:
-    // halving the stages cuts throughput ~40 %).  The producer therefore prefetches B tiles into L2 PF k-blocks ahead
-    // (and the head of its next tile), which costs no shared memory.
-    constexpr int PF = SLAM_GEMM_PREFETCH;
-    auto prefetch_b = [&](int n_tile_pf, int kb_pf) {
-      if (kb_pf < p.kb1) tma_prefetch_l2_2d(&tmB, kb_pf * GEMM_BK, n_tile_pf * BLOCK_N);
-      else tma_prefetch_l2_2d(&tmB2, (kb_pf - p.kb1) * GEMM_BK, n_tile_pf * BLOCK_N);
-    };
-    uint32_t kc = 0;
-    if (PF > 0 && p.ksplit == 1 && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
-      const int n_first = static_cast<int>(blockIdx.x) / p.num_m_tiles;
-      for (int kb = 0; kb < PF && kb < nkb; ++kb) prefetch_b(n_first, kb);
-    }
-    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-      const int tile = item / p.ksplit;
-      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
-      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
-      const int m_tile = tile % p.num_m_tiles;
-      const int n_tile = tile / p.num_m_tiles;
-      const int next_tile = (PF > 0 && p.ksplit == 1) ? item + static_cast<int>(gridDim.x) : total_tiles;
-      for (int kb = kb_begin; kb < kb_end; ++kb, ++kc) {
-        const uint32_t stage = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1u;
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), full_u = smem_u32(full_bar);
+    uint32_t stage = 0, ph = 0;
+    GemmSchedule sched(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+    GemmSeg sg;
+    while (sched.next(sg)) {
+      const int row_a = (sg.tile % p.num_m_tiles) * BLOCK_M;
+      const int row_b = (sg.tile / p.num_m_tiles) * BLOCK_N;
+      for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], ph ^ 1u);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          void* dA = sA + stage * Cfg::A_BYTES;
-          void* dB = sB + stage * Cfg::B_BYTES;
-          if (kb < p.kb1) {
-            tma_load_2d(dA, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * BLOCK_M);
-            tma_load_2d(dB, &tmB, &full_bar[stage], kb * GEMM_BK, n_tile * BLOCK_N);
-          } else {
-            const int k2 = kb - p.kb1;
-            tma_load_2d(dA, &tmA2, &full_bar[stage], k2 * GEMM_BK, m_tile * BLOCK_M);
-            tma_load_2d(dB, &tmB2, &full_bar[stage], k2 * GEMM_BK, n_tile * BLOCK_N);
-          }
-          if (PF > 0 && p.ksplit == 1) {
-            if (kb + PF < nkb) prefetch_b(n_tile, kb + PF);
-            else if (next_tile < total_tiles) prefetch_b(next_tile / p.num_m_tiles, kb + PF - nkb);
-          }
+        const uint32_t fb = full_u + stage * 8;
+        mbar_arrive_expect_tx_elect(fb, Cfg::A_BYTES + Cfg::B_BYTES);
+        if (kb < p.kb1) {
+          tma_load_2d_elect(sA_u + stage * Cfg::A_BYTES, &tmA, fb, kb * GEMM_BK, row_a);
+          tma_load_2d_elect(sB_u + stage * Cfg::B_BYTES, &tmB, fb, kb * GEMM_BK, row_b);
+        } else {
+          const int k2 = kb - p.kb1;
+          tma_load_2d_elect(sA_u + stage * Cfg::A_BYTES, &tmA2, fb, k2 * GEMM_BK, row_a);
+          tma_load_2d_elect(sB_u + stage * Cfg::B_BYTES, &tmB2, fb, k2 * GEMM_BK, row_b);
         }
-        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ MMA issuer (whole warp; see "warp-uniform issue helpers")
     constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N);
-    uint32_t kc = 0;
+    // lane s keeps the descriptor low words of ring slot s; a shuffle by the (uniform) stage index yields uniform operands
+    const uint32_t my_a = sw128_kmajor_desc_lo(smem_u32(sA) + (lane < STAGES ? lane : 0) * Cfg::A_BYTES);
+    const uint32_t my_b = sw128_kmajor_desc_lo(smem_u32(sB) + (lane < STAGES ? lane : 0) * Cfg::B_BYTES);
+    const uint32_t empty_u = smem_u32(empty_bar), tfull_u = smem_u32(tfull_bar);
+    uint32_t stage = 0, ph = 0;
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
-      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
-      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
+    GemmSchedule sched(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+    GemmSeg sg;
+    for (; sched.next(sg); ++it) {
       const uint32_t acc = it % ACC_STAGES;
       const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tempty_bar[acc], aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * HALVES * BLOCK_N;
-      for (int kb = kb_begin; kb < kb_end; ++kb, ++kc) {
-        const uint32_t stage = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1u;
+      for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         mbar_wait(&full_bar[stage], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128-B swizzle span: +2 in 16-B units;
-            // the second M=128 half of a 256-row A tile starts 128 rows * 128 B = 16 KB further (+1024 units)
-#pragma unroll
-            for (int hf = 0; hf < HALVES; ++hf)
-              umma_bf16(d_tmem + hf * BLOCK_N, a_desc + 1024u * hf + 2u * k, b_desc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) umma_commit(&tfull_bar[acc]);
+        const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, stage);
+        const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, stage);
+        const uint32_t accum = kb > sg.kb_begin ? 1u : 0u;
+        umma_kblock_1(d_tmem, a_lo, b_lo, idesc, accum);
+        if constexpr (HALVES == 2) umma_kblock_1(d_tmem + BLOCK_N, a_lo + 1024u, b_lo, idesc, accum);   // rows 128..255: A tile + 16 KB
+        umma_commit_elect(empty_u + stage * 8);
+        if (kb == sg.kb_end - 1) umma_commit_elect(tfull_u + acc * 8);
+        if (++stage == STAGES) {
+          stage = 0;
+          ph ^= 1u;
         }
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
-      const int tile = item / p.ksplit;
-      const int m_tile = tile % p.num_m_tiles;
-      const int n_tile = tile / p.num_m_tiles;
+    GemmSchedule sched(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+    GemmSeg sg;
+    const int cta = static_cast<int>(blockIdx.x);
+    for (; sched.next(sg); ++it) {
+      const int m_tile = sg.tile % p.num_m_tiles;
+      const int n_tile = sg.tile / p.num_m_tiles;
       const uint32_t acc = it % ACC_STAGES;
       const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tfull_bar[acc], aph);
@@ -223,7 +189,86 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // registers again with (8 rows x 4 column-pieces) per warp instruction, so that global stores and residual loads
       // touch whole 32-byte sectors (64 B of bf16 per row) instead of one 16-byte piece of 32 different rows.
       float* stg = epi_stage + q * (32 * Cfg::EPI_PITCH);
-      const int piece = lane & 3;
+      if (sg.kind == 1) {
+        if constexpr (HALVES == 1) {
+          // ---- tail tile: exchange partial accumulators with the other k-slices of this tile (CTAs base .. base + S - 1)
+          constexpr int NCH = BLOCK_N / 32;
+          const int S = p.tail_slices, slice = cta % S, base = cta - slice;
+          const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+          const int row_base = m_tile * BLOCK_M + q * 32;
+          // a slot is [quarter q][chunk c][row][32 floats]: 4 KB blocks, 16-byte pieces XOR-swizzled by (row % 8) so that the
+          // owner's thread-per-row reads of the block from shared memory are bank-conflict free
+          auto block_of = [&](int cta_id, int c) { return p.sk_partials + (static_cast<long long>(cta_id) * 4 + q) * (NCH * 1024) + c * 1024; };
+          // pass 1: publish the chunks other slices finish
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            if (c % S == slice) continue;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(block_of(cta, c) + lane * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+          __threadfence();            // every lane's partial stores are visible device-wide before the flag
+          __syncwarp();
+          // the tail item is the last work of the CTA: the operand ring is idle, 48 KB of it per epilogue warp receive the peers' blocks
+          float* xbuf = reinterpret_cast<float*>(smem + q * (48 * 1024));
+          if (lane == 0) {
+            sk_flag_publish(p.sk_flags + cta * 4 + q, p.sk_epoch);
+            for (int j = 0; j < S; ++j)
+              if (j != slice) sk_flag_wait(p.sk_flags + (base + j) * 4 + q, p.sk_epoch);
+            fence_proxy_async_global();   // peers' generic-proxy stores (acquired above) -> visible to the bulk-copy engine
+            uint32_t blocks = 0;
+            for (int c = slice; c < NCH; c += S) blocks += static_cast<uint32_t>(S - 1);
+            mbar_arrive_expect_tx(&xchg_bar[q], blocks * 4096u);
+            uint32_t slot = 0;
+            for (int c = slice; c < NCH; c += S)
+              for (int j = 0; j < S; ++j)
+                if (j != slice) bulk_load_1d(xbuf + (slot++) * 1024, block_of(base + j, c), 4096u, &xchg_bar[q]);
+          }
+          __syncwarp();
+          mbar_wait(&xchg_bar[q], 0);
+          // pass 2: finish this slice's chunks: sum in slice order (own accumulator at position `slice`), then the epilogue
+          uint32_t slot = 0;
+#pragma unroll 1
+          for (int c = slice; c < NCH; c += S) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            float accv[32];
+            bool first = true;
+            for (int j = 0; j < S; ++j) {
+              if (j == slice) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) accv[e] = first ? __uint_as_float(r[e]) : accv[e] + __uint_as_float(r[e]);
+              } else {
+                const float4* src = reinterpret_cast<const float4*>(xbuf + (slot++) * 1024 + lane * 32);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 v = src[jj ^ (lane & 7)];
+                  accv[4 * jj] = first ? v.x : accv[4 * jj] + v.x;
+                  accv[4 * jj + 1] = first ? v.y : accv[4 * jj + 1] + v.y;
+                  accv[4 * jj + 2] = first ? v.z : accv[4 * jj + 2] + v.z;
+                  accv[4 * jj + 3] = first ? v.w : accv[4 * jj + 3] + v.w;
+                }
+              }
+              first = false;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + j * 4) = make_float4(accv[4 * j], accv[4 * j + 1], accv[4 * j + 2], accv[4 * j + 3]);
+            __syncwarp();
+            gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
+            __syncwarp();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int hf = 0; hf < HALVES; ++hf) {
         const int row_base = m_tile * BLOCK_M + hf * 128 + q * 32;
@@ -243,54 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
-          const int col = n0 + c * 32 + piece * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = i * 8 + (lane >> 2);
-            const int row = row_base + rr;
-            if (row >= p.M || col >= p.N) continue;
-            const float4 x0 = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_PITCH + piece * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_PITCH + piece * 8 + 4);
-            float v[8] = {x0.x * p.alpha, x0.y * p.alpha, x0.z * p.alpha, x0.w * p.alpha,
-                          x1.x * p.alpha, x1.y * p.alpha, x1.z * p.alpha, x1.w * p.alpha};
-            if (p.bias != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.act == 1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-            } else if (p.act == 2) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-            }
-            if (p.residual != nullptr) {
-              const uint4 rsd = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-              const float2 r0 = unpack_bf16x2(rsd.x), r1 = unpack_bf16x2(rsd.y), r2 = unpack_bf16x2(rsd.z),
-                           r3 = unpack_bf16x2(rsd.w);
-              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-            }
-            if (p.ksplit > 1) {
-              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) atomicAdd(o + e, v[e]);      // k-slices merge into the zero-initialised fp32 output
-            } else if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-              uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]);
-              pk.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(o) = pk;
-            }
-          }
+          gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
           __syncwarp();
         }
       }
@@ -348,6 +346,66 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t k, 
   return 0;
 }
 
+static void fill_kparams(const slam_gemm_args* g, int block_m, int block_n, GemmKParams& p) {
+  p.M = g->m;
+  p.N = g->n;
+  p.kb1 = static_cast<int>(ceil_div(g->k1, GEMM_BK));
+  p.kb2 = g->k2 > 0 ? static_cast<int>(ceil_div(g->k2, GEMM_BK)) : 0;
+  p.num_m_tiles = static_cast<int>(ceil_div(g->m, block_m));
+  p.num_n_tiles = static_cast<int>(ceil_div(g->n, block_n));
+  p.out = g->out;
+  p.ldo = g->ldo;
+  p.out_f32 = g->out_f32;
+  p.act = g->act;
+  p.bias = g->bias;
+  p.residual = reinterpret_cast<const bf16*>(g->residual);
+  p.ldr = g->ldr;
+  p.alpha = g->alpha;
+  p.ksplit = g->split_k > 1 ? g->split_k : 1;
+  const int nkb_total = p.kb1 + p.kb2;
+  if (p.ksplit > nkb_total) p.ksplit = nkb_total;
+  p.kb_per_split = static_cast<int>(ceil_div(nkb_total, p.ksplit));
+  p.ksplit = static_cast<int>(ceil_div(nkb_total, p.kb_per_split));   // no empty k-slices
+  p.tail_tiles = 0;
+  p.tail_slices = 1;
+  p.tail_kb = nkb_total;
+  p.sk_partials = nullptr;
+  p.sk_epoch = 0;
+  p.sk_flags = nullptr;
+}
+
+constexpr int64_t SK_FLAG_BYTES = 4096;                       // [SMs][4] u32 flags at the head of the workspace
+static int64_t sk_workspace_bytes() { return SK_FLAG_BYTES + static_cast<int64_t>(num_sms()) * 128 * 256 * 4; }
+
+// Tail-split plan for 128-row tiles: with T tiles on G = #SMs CTAs the last wave has R = T mod G tiles; cutting each into
+// s = floor(G / R) k-slices (capped: the owner CTA reads s - 1 partial tiles back from L2) keeps R * s CTAs busy for 1/s of a
+// tile time instead of R CTAs for a whole one.
+static void plan_tail_split(const slam_gemm_args* g, GemmKParams& p, int block_m, int block_n) {
+  if (g->workspace == nullptr || g->tail_split < 0 || block_m != 128 || p.ksplit > 1) return;
+  if (g->workspace_bytes < sk_workspace_bytes() || (reinterpret_cast<uintptr_t>(g->workspace) & 15) != 0) return;
+  const int G = num_sms();
+  const int T = p.num_m_tiles * p.num_n_tiles;
+  const int nkb = p.kb1 + p.kb2;
+  const int R = T % G;
+  if (R == 0) return;
+  int s = G / R;
+  int max_slices = g->tail_split > 1 ? g->tail_split : 8;
+  if (max_slices > 8) max_slices = 8;                   // the exchange buffers (48 KB per epilogue warp) hold ceil(NCH / s) * (s - 1) <= 12 blocks
+  if (max_slices > block_n / 32) max_slices = block_n / 32;
+  if (s > max_slices) s = max_slices;
+  if (s > nkb / 4) s = nkb / 4;              // at least 4 k-blocks per slice
+  if (s < 2) return;
+  p.tail_tiles = R;
+  p.tail_kb = static_cast<int>(ceil_div(nkb, s));
+  p.tail_slices = static_cast<int>(ceil_div(nkb, p.tail_kb));
+  // flag value of this launch: never 0, distinct from every recent launch (the workspace keeps old epochs between calls);
+  // seeded from the clock so that a re-loaded library does not repeat the sequence of a previous instance on the same buffer
+  static std::atomic<unsigned int> epoch{static_cast<unsigned int>(std::chrono::steady_clock::now().time_since_epoch().count()) | 1u};
+  unsigned int e = epoch.fetch_add(1u) + 1u;
+  if (e == 0u) e = epoch.fetch_add(1u) + 1u;
+  p.sk_epoch = e;
+}
+
 template <int BLOCK_M, int BLOCK_N>
 static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_M, BLOCK_N>;
@@ -374,27 +432,15 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
     tmB2 = tmB;
   }
   GemmKParams p;
-  p.M = g->m;
-  p.N = g->n;
-  p.kb1 = static_cast<int>(ceil_div(g->k1, GEMM_BK));
-  p.kb2 = g->k2 > 0 ? static_cast<int>(ceil_div(g->k2, GEMM_BK)) : 0;
-  p.num_m_tiles = static_cast<int>(ceil_div(g->m, GEMM_BM));
-  p.num_n_tiles = static_cast<int>(ceil_div(g->n, BLOCK_N));
-  p.out = g->out;
-  p.ldo = g->ldo;
-  p.out_f32 = g->out_f32;
-  p.act = g->act;
-  p.bias = g->bias;
-  p.residual = reinterpret_cast<const bf16*>(g->residual);
-  p.ldr = g->ldr;
-  p.alpha = g->alpha;
-  p.ksplit = g->split_k > 1 ? g->split_k : 1;
-  const int nkb_total = p.kb1 + p.kb2;
-  if (p.ksplit > nkb_total) p.ksplit = nkb_total;
-  p.kb_per_split = static_cast<int>(ceil_div(nkb_total, p.ksplit));
-  p.ksplit = static_cast<int>(ceil_div(nkb_total, p.kb_per_split));   // no empty k-slices
+  fill_kparams(g, GEMM_BM, BLOCK_N, p);
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  plan_tail_split(g, p, BLOCK_M, BLOCK_N);
+  if (p.tail_tiles > 0) {
+    grid = num_sms();
+    p.sk_flags = reinterpret_cast<unsigned int*>(g->workspace);
+    p.sk_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g->workspace) + SK_FLAG_BYTES);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -414,38 +460,101 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   return 0;
 }
 
-// Tile choice fitted to B200 measurements (profiles/r01_gemm_bench_v2.json).  Returns BLOCK_M * 1000 + BLOCK_N.
-//  * 128-row tiles have two TMEM accumulator stages (epilogue overlaps the next tile): pick 256 vs 192 columns by wave
-//    quantisation, cost = ceil(tiles / SMs) * BLOCK_N * penalty (192 re-reads A slightly more often; 128 is smem-bound).
-//  * 256x256 tiles (two M=128 accumulators sharing each B tile) need 1/3 less L2->SM traffic per MMA cycle but expose their
-//    epilogue once per tile: they win only when the whole GEMM is a single wave and K is long enough to amortise it
-//    (down_proj, the gate/up dgrad, the encoder fc2: +8..12 %); with several waves they lose 10-20 %.
-static int pick_tile(int m, int n, int k) {
-  if (n <= 64) return 128 * 1000 + 64;
-  if (n < 192) return 128 * 1000 + 128;
-  const int sms = num_sms();
-  if (k >= 5000 && n >= 256) {   // one well-filled wave of 256-row tiles: prefer the width that uses the most SMs
-    const int64_t t224 = ceil_div(m, 256) * ceil_div(n, 224), t256 = ceil_div(m, 256) * ceil_div(n, 256);
-    if (t224 <= sms && t224 > t256 && t224 * 10 >= sms * 6) return 256 * 1000 + 224;
-    if (t256 <= sms && t256 * 10 >= sms * 6) return 256 * 1000 + 256;
+template <int BLOCK_N>
+static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm(pair): cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
   }
-  const int64_t mt = ceil_div(m, 128);
-  const int cands[3] = {256, 192, 128};
-  const double pen[3] = {1.0, 1.04, 1.5};
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int rc;
+  if ((rc = make_tmap(&tmA, g->a, g->m, g->k1, g->lda, 128)) != 0) return rc;
+  if ((rc = make_tmap(&tmB, g->b, g->n, g->k1, g->ldb, BLOCK_N / 2)) != 0) return rc;
+  if (g->k2 > 0) {
+    if ((rc = make_tmap(&tmA2, g->a2, g->m, g->k2, g->lda2, 128)) != 0) return rc;
+    if ((rc = make_tmap(&tmB2, g->b2, g->n, g->k2, g->ldb2, BLOCK_N / 2)) != 0) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+  GemmKParams p;
+  fill_kparams(g, 256, BLOCK_N, p);
+  const int items = p.num_m_tiles * p.num_n_tiles * p.ksplit;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = items < max_pairs ? items : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);                // cluster dims (2,1,1) are compiled into the kernel
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_pair_kernel<BLOCK_N>, tmA, tmB, tmA2, tmB2, p);
+  if (le != cudaSuccess) {
+    set_error("slam_gemm_bf16(pair): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return static_cast<int>(le);
+  }
+  SLAM_LAUNCH_CHECK("slam_gemm_bf16.pair");
+  return 0;
+}
+
+// Tile choice.  Fitted to SUSTAINED (power-capped, ~1000 W) B200 measurements of the step's shapes, where throughput is set by
+// energy per flop as much as by tensor-pipe occupancy (profiles/r01_gemm_power.log).  Every configuration gives each SM 128
+// accumulator rows per tile, so a kernel's time is modelled as
+//     waves x BLOCK_N x pen,   waves = full waves + cost of the last partial wave (1, or 1/s + 0.2 with the tail split),
+// with one measured relative cost per flop `pen` per configuration: CTA pairs (cta_group::2) move 1/3 fewer operand bytes per
+// MMA cycle and are 7-14 % cheaper, but they need M in multiples of 256 (a 1604-row activation wastes 10 % of a pair grid).
+// The model reproduces the measured ranking on all 14 GEMM shapes of the step.  Returns the slam_gemm_args.block_n code.
+struct TileCand {
+  int code, rows, bn;
+  double pen;
+  bool pair;
+};
+static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair) {
+  if (n <= 64) return 128 * 1000 + 64;
+  static const TileCand cands[] = {
+      {128256, 128, 256, 1.000, false}, {128192, 128, 192, 0.977, false}, {128128, 128, 128, 1.170, false},
+      {2000256, 256, 256, 0.882, true}, {2000224, 256, 224, 0.864, true}, {2000192, 256, 192, 0.928, true}, {2000160, 256, 160, 1.010, true},
+  };
+  const int sms = num_sms();
+  const int nkb = static_cast<int>(ceil_div(k, GEMM_BK));
   double best = 1e30;
-  int best_bn = 256;
-  for (int i = 0; i < 3; ++i) {
-    if (cands[i] > n && i < 2) continue;
-    const double c = static_cast<double>(ceil_div(mt * ceil_div(n, cands[i]), sms)) * cands[i] * pen[i];
-    if (c < best) {
-      best = c;
-      best_bn = cands[i];
+  int best_code = 128256;
+  for (const TileCand& c : cands) {
+    if (c.pair && !allow_pair) continue;
+    if (c.bn >= n + 64) continue;                                  // more than two chunks of padding columns
+    const int64_t tiles = ceil_div(m, c.rows) * ceil_div(n, c.bn);
+    const int units = c.pair ? sms / 2 : sms;
+    const int64_t full = tiles / units, rem = tiles % units;
+    double tail = rem == 0 ? 0.0 : 1.0;
+    if (!c.pair && tail_split && rem > 0) {
+      int64_t sl = units / rem;
+      if (sl > 8) sl = 8;
+      if (sl > c.bn / 32) sl = c.bn / 32;
+      if (sl > nkb / 4) sl = nkb / 4;
+      if (sl >= 2) tail = 1.0 / static_cast<double>(sl) + 0.2;
+    }
+    const double cost = (static_cast<double>(full) + tail) * c.bn * c.pen;
+    if (cost < best) {
+      best = cost;
+      best_code = c.code;
     }
   }
-  return 128 * 1000 + best_bn;
+  return best_code;
 }
 
 }  // namespace slam
+
+extern "C" int64_t slam_gemm_workspace_bytes(void) { return slam::sk_workspace_bytes(); }
 
 extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   using namespace slam;
@@ -462,8 +571,8 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
                  "gemm: split_k needs a zero-initialised f32 output and no bias/activation/residual");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
-  if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2);
-  if (tile < 1000) tile += 128 * 1000;
+  if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1, g->split_k <= 1);
+  if (tile < 1000) tile += 128 * 1000;   // (2000000 + BLOCK_N = CTA-pair kernel)
   switch (tile) {
     case 128256: return launch_gemm<128, 256>(g, st);
     case 128192: return launch_gemm<128, 192>(g, st);
@@ -471,8 +580,11 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
     case 128064: return launch_gemm<128, 64>(g, st);
     case 256256: return launch_gemm<256, 256>(g, st);
     case 256224: return launch_gemm<256, 224>(g, st);
-    case 256192: return launch_gemm<256, 192>(g, st);
-    case 256128: return launch_gemm<256, 128>(g, st);
+    case 2000256: return launch_gemm_pair<256>(g, st);   // CTA-pair kernels (cta_group::2), pair tile 256 x BLOCK_N
+    case 2000224: return launch_gemm_pair<224>(g, st);
+    case 2000192: return launch_gemm_pair<192>(g, st);
+    case 2000160: return launch_gemm_pair<160>(g, st);
+    case 2000128: return launch_gemm_pair<128>(g, st);
     default: set_error("gemm: unsupported tile %d", tile); return -1;
   }
 }

@@ -1,0 +1,197 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM: two CTAs on the two SMs of one TPC compute one 256 x BLOCK_N tile.
+// Each CTA stages ITS 128 rows of A and ITS half (BLOCK_N/2 rows) of the B tile; the leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 with M = 256, which reads A from both CTAs' shared memory, shares the two B halves across the pair
+// and accumulates rows [0,128) in the leader's TMEM and rows [128,256) in the peer's.  Per MMA cycle an SM therefore stages
+// 2/3 of the bytes of the 128 x 256 single-CTA tile (16 KB A + 16 KB B-half instead of 16 KB + 32 KB per k-block), which is
+// what bounds the single-CTA mainloop (shared-memory fill + operand read bandwidth, and bytes in flight per SM).
+//
+// Synchronisation (offsets are identical in both CTAs):
+//   full[s]    leader only; 1 arrival (leader producer, expect_tx = both CTAs' stage bytes); both producers' TMA loads
+//              complete_tx on it (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address);
+//   empty[s]   in each CTA; tcgen05.commit.cta_group::2 multicast from the leader frees the slot in both CTAs;
+//   tfull[a]   in each CTA; multicast commit publishes the accumulator to both epilogues;
+//   tempty[a]  leader only; 8 arrivals = 4 epilogue warps of each CTA (the peer arrives remotely through the cluster window).
+#pragma once
+#include "gemm_common.cuh"
+
+namespace slam {
+
+template <int BLOCK_N>
+struct GemmPairCfg {
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int A_BYTES = 128 * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
+  static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int EPI_BYTES = 4 * 32 * GEMM_EPI_PITCH * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert((BLOCK_N / 2) % 8 == 0 && BLOCK_N % 16 == 0, "B half must be whole 8-row swizzle groups");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = static_cast<int>(blockIdx.x >> 1);
+  const int npairs = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kb2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int total_items = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // num_m_tiles counts 256-row pair tiles
+  const int nkb = p.kb1 + p.kb2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs; whole warp, elected lane issues)
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const uint32_t full_leader = mapa_shared(smem_u32(full_bar), 0);
+    uint32_t stage = 0, ph = 0;
+    for (int item = pair; item < total_items; item += npairs) {
+      const int tile = item / p.ksplit;
+      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
+      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
+      const int row_a = (tile % p.num_m_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int row_b = (tile / p.num_m_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], ph ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+        const uint32_t fb = full_leader + stage * 8;
+        if (kb < p.kb1) {
+          tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA, fb, kb * GEMM_BK, row_a);
+          tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB, fb, kb * GEMM_BK, row_b);
+        } else {
+          const int k2 = kb - p.kb1;
+          tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA2, fb, k2 * GEMM_BK, row_a);
+          tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB2, fb, k2 * GEMM_BK, row_b);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only; whole warp, uniform operands)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+      const uint32_t my_a = sw128_kmajor_desc_lo(smem_u32(sA) + (lane < STAGES ? lane : 0) * Cfg::A_BYTES);
+      const uint32_t my_b = sw128_kmajor_desc_lo(smem_u32(sB) + (lane < STAGES ? lane : 0) * Cfg::B_BYTES);
+      const uint32_t empty_u = smem_u32(empty_bar), tfull_u = smem_u32(tfull_bar);
+      uint32_t stage = 0, ph = 0;
+      uint32_t it = 0;
+      for (int item = pair; item < total_items; item += npairs, ++it) {
+        const int kb_begin = (item % p.ksplit) * p.kb_per_split;
+        const int kb_end = min(nkb, kb_begin + p.kb_per_split);
+        const uint32_t acc = it % ACC_STAGES;
+        const uint32_t aph = (it / ACC_STAGES) & 1u;
+        mbar_wait_cluster(&tempty_bar[acc], aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], ph);
+          tc_fence_after();
+          const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, stage);
+          const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, stage);
+          umma_kblock_pair(d_tmem, a_lo, b_lo, idesc, kb > kb_begin ? 1u : 0u);
+          umma_commit_pair_elect(empty_u + stage * 8);
+          if (kb == kb_end - 1) umma_commit_pair_elect(tfull_u + acc * 8);
+          if (++stage == STAGES) {
+            stage = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (both CTAs, each drains its own 128 rows)
+    const int q = warp - 4;
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    uint32_t it = 0;
+    for (int item = pair; item < total_items; item += npairs, ++it) {
+      const int tile = item / p.ksplit;
+      const int m_tile = tile % p.num_m_tiles;
+      const int n_tile = tile / p.num_m_tiles;
+      const uint32_t acc = it % ACC_STAGES;
+      const uint32_t aph = (it / ACC_STAGES) & 1u;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+      const int n0 = n_tile * BLOCK_N;
+      float* stg = epi_stage + q * (32 * GEMM_EPI_PITCH);
+      const int row_base = m_tile * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_leader0 + acc * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * GEMM_EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // no CTA of the pair may exit (or free TMEM) while the other can still touch its memory
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace slam

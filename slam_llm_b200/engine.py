@@ -34,9 +34,13 @@ def _round_up(x: int, m: int) -> int:
 
 def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch.Tensor:
     """bf16 out = a @ b.T (+ a2 @ b2.T) for products with few output tiles but a long K (LoRA rank-64 products, lm_head dgrad):
-    split-K over otherwise idle SMs (fp32 atomics into a zeroed buffer), then one cast back to bf16."""
+    wide outputs (N >= 256) use the GEMM's own tail split (k-slices on idle SMs, deterministic exchange, bf16 epilogue);
+    thin ones (rank-64 LoRA products: two 32-column chunks per tile) split K over otherwise idle SMs with fp32 atomics into a
+    zeroed buffer, then one cast back to bf16."""
     M, K = a.shape
     N = b.shape[0]
+    if N >= 256:
+        return ops.gemm(a, b, a2=a2, b2=b2)
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 64 else 1)
     nkb = (K + 63) // 64 + ((a2.shape[1] + 63) // 64 if a2 is not None else 0)
     split = min(8, nkb // 4, max(1, 148 // tiles))

@@ -32,6 +32,8 @@ class GemmArgs(C.Structure):
         ("m", _i32), ("n", _i32),
         ("block_n", _i32),
         ("split_k", _i32),
+        ("workspace", _vp), ("workspace_bytes", _i64),
+        ("tail_split", _i32), ("reserved", _i32),
     ]
 
 
@@ -62,6 +64,7 @@ _SIGS = {
     "slam_last_error": [],
     "slam_launch_count": [],
     "slam_gemm_bf16": [C.POINTER(GemmArgs), _vp],
+    "slam_gemm_workspace_bytes": [],
     "slam_wgrad_thin": [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp],
     "slam_logmel": [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "slam_conv_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
@@ -91,7 +94,7 @@ _SIGS = {
     "slam_pack2d": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _vp],
     "slam_add_bf16": [_vp, _vp, _vp, _i64, _vp],
 }
-_RESTYPES = {"slam_last_error": C.c_char_p, "slam_launch_count": _i64}
+_RESTYPES = {"slam_last_error": C.c_char_p, "slam_launch_count": _i64, "slam_gemm_workspace_bytes": _i64}
 
 _lib = None
 
@@ -118,8 +121,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.slam_abi_version() != 1:
-        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 1")
+    if lib.slam_abi_version() != 2:
+        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import os
+
 import torch
 
 from . import lib as _l
@@ -53,10 +55,25 @@ def set_gemm_event_log(log) -> None:
 
 
 # ------------------------------------------------------------------------------------------- GEMM
+_GEMM_WS: dict = {}
+_TAIL_SPLIT_DEFAULT = int(os.environ.get("SLAM_TAIL_SPLIT", "0"))     # experiments: -1 disables the GEMM tail split globally
+
+
+def _gemm_workspace(device: torch.device) -> torch.Tensor:
+    """Tail-split exchange buffer: zeroed once, one per (device, stream) - the library owns it between calls on that stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_l.load().slam_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1) -> torch.Tensor:
-    """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16."""
+         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1, tail_split: int = 0) -> torch.Tensor:
+    """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16.
+    tail_split: 0 = automatic, -1 = off, n > 1 = at most n k-slices per tail tile."""
     _req(a, BF16, "gemm.a"); _req(b, BF16, "gemm.b")
     M, K1 = a.shape
     N = b.shape[0]
@@ -98,6 +115,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     g.m, g.n = M, N
     g.block_n = block_n
     g.split_k = split_k
+    if tail_split == 0:
+        tail_split = _TAIL_SPLIT_DEFAULT
+    g.tail_split = tail_split
+    if tail_split >= 0 and split_k <= 1:
+        ws = _gemm_workspace(a.device)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    else:
+        g.workspace, g.workspace_bytes = None, 0
     if _GEMM_LOG is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

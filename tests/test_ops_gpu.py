@@ -43,7 +43,9 @@ def cos_sim(a, b):
     (1600, 4096, 4096, 0), (300, 384, 1920, 0), (308, 2048, 512, 256),
     (1, 64, 64, 64), (257, 1280, 1280, 128), (1200, 6144, 4096, 256), (77, 5120, 240, 0),
     (1600, 4096, 4096, 192), (300, 200, 512, 192), (1600, 6144, 4096, 192),
-    (1600, 4096, 4096, 256256), (1600, 4096, 6144, 256224), (300, 384, 1920, 256192), (6000, 1280, 1280, 256256), (257, 520, 640, 256128), (129, 256, 64, 256256),
+    (1600, 4096, 4096, 256256), (1600, 4096, 6144, 256224), (6000, 1280, 1280, 256256), (129, 256, 64, 256256),
+    # CTA-pair kernels (cta_group::2): 256 x BLOCK_N per SM pair
+    (1604, 4096, 4096, 2000256), (6000, 1280, 1280, 2000224), (300, 384, 1920, 2000192), (257, 520, 640, 2000160), (129, 256, 64, 2000128), (1, 64, 64, 2000128),
 ])
 def test_gemm_plain(ops, M, N, K, bn):
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
@@ -81,7 +83,7 @@ def test_gemm_epilogue(ops, act):
     assert rel_err(out, ref) < 6e-3
 
 
-@pytest.mark.parametrize("tile", [0, 128256, 128192, 256256, 256192])
+@pytest.mark.parametrize("tile", [0, 128256, 128192, 256256, 2000256, 2000224])
 def test_gemm_dual_segment_lora(ops, tile):
     # y = x W^T + (x A^T)(s B)^T accumulated in one TMEM tile
     M, N, K, R = 1600, 6144, 4096, 64
@@ -92,6 +94,22 @@ def test_gemm_dual_segment_lora(ops, tile):
     assert rel_err(out, ref) < 6e-3
     only_base = ops.gemm(x, w)
     assert rel_err(only_base, ref) > 2e-2  # the second segment really contributes
+
+
+@pytest.mark.parametrize("M,N,K,tile", [(1604, 4096, 4096, 128256), (1604, 6144, 4096, 128256), (308, 4096, 32064, 128256), (1604, 4096, 4096, 128192),
+                                        (300, 776, 1280, 128128), (77, 264, 256, 128256)])
+def test_gemm_tail_split(ops, M, N, K, tile):
+    """Last partial wave cut into k-slices (partials exchanged through the workspace): same result as the plain schedule up to
+    fp32 summation order, bit-identical from run to run, full epilogue applied."""
+    a, b = rnd(M, K, seed=90), rnd(N, K, scale=0.05, seed=91)
+    bias, res = rnd(N, seed=92).float(), rnd(M, N, seed=93)
+    plain = ops.gemm(a, b, bias=bias, residual=res, act=1, block_n=tile, tail_split=-1)
+    outs = [ops.gemm(a, b, bias=bias, residual=res, act=1, block_n=tile, tail_split=8) for _ in range(3)]
+    ref = torch.nn.functional.gelu(a.float() @ b.float().t() + bias) + res.float()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert rel_err(outs[0], ref) < 6e-3 and rel_err(outs[0], plain.float()) < 6e-3
+    out32 = ops.gemm(a, b, out_f32=True, block_n=tile, tail_split=8)
+    assert rel_err(out32, a.float() @ b.float().t()) < 1e-4
 
 
 @pytest.mark.parametrize("M,N,K,K2,split", [(1600, 64, 4096, 0, 8), (308, 4096, 12800, 0, 3), (1600, 64, 6144, 64, 5), (257, 512, 640, 0, 4)])

@@ -7,10 +7,10 @@ import torch
 from slam_llm_b200 import ops
 
 SHAPES = [  # (M, N, K, K2, tag)
-    (1600, 6144, 4096, 64, "qkv+lora"), (1600, 4096, 4096, 0, "o"), (1600, 28672, 4096, 0, "gate_up"),
-    (1600, 4096, 14336, 0, "down"), (1600, 14336, 4096, 0, "d_down"), (1600, 4096, 28672, 0, "d_gate_up"),
+    (1604, 6144, 4096, 64, "qkv+lora"), (1604, 4096, 4096, 0, "o"), (1604, 28672, 4096, 0, "gate_up"),
+    (1604, 4096, 14336, 0, "down"), (1604, 14336, 4096, 0, "d_down"), (1604, 4096, 28672, 0, "d_gate_up"),
     (6000, 3840, 1280, 0, "enc_qkv"), (6000, 5120, 1280, 0, "enc_fc1"), (6000, 1280, 5120, 0, "enc_fc2"),
-    (308, 128256, 4096, 0, "lm_head"), (308, 4096, 128256, 0, "d_lm_head"), (1600, 64, 4096, 0, "lora_T"),
+    (308, 128256, 4096, 0, "lm_head"), (308, 4096, 128256, 0, "d_lm_head"), (1604, 64, 4096, 0, "lora_T"),
 ]
 
 def bench(fn, iters=20):
@@ -36,9 +36,12 @@ for M, N, K, K2, tag in SHAPES:
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     row = {"tag": tag, "M": M, "N": N, "K": K, "K2": K2}
     flops = 2.0 * M * N * (K + K2)
-    for bn in (0, 128256, 128192, 256256, 256224) if N >= 256 else (0,):
-        t = bench(lambda: ops.gemm(a, b, a2=a2, b2=b2, out=out, block_n=bn))
+    for bn in (0, 128256, 128192, 256256, 256224, 2000256) if N >= 256 else (0,):
+        t = bench(lambda: ops.gemm(a, b, a2=a2, b2=b2, out=out, block_n=bn, tail_split=-1))
         row[f"slam_bn{bn}_ms"] = round(t, 4); row[f"slam_bn{bn}_tflops"] = round(flops / t / 1e9, 1)
+    for bn, sk in ((0, 0), (128256, 0), (128256, 2), (128256, 8), (128192, 0)) if N >= 256 else ((0, 0),):
+        t = bench(lambda: ops.gemm(a, b, a2=a2, b2=b2, out=out, block_n=bn, tail_split=sk))
+        row[f"slam_sk{sk}_bn{bn}_ms"] = round(t, 4); row[f"slam_sk{sk}_bn{bn}_tflops"] = round(flops / t / 1e9, 1)
     t = bench(lambda: torch.matmul(a, b.t(), out=out))
     row["cublas_ms"] = round(t, 4); row["cublas_tflops"] = round(2.0 * M * N * K / t / 1e9, 1)
     res.append(row)
