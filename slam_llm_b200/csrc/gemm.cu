@@ -48,8 +48,7 @@ struct GemmCfg {
   static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);  // power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_PITCH = GEMM_EPI_PITCH;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                 // one 32x32 fp32 chunk per epilogue warp
+  static constexpr int EPI_BYTES = GEMM_EPI_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 };
@@ -72,9 +71,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* xchg_bar = tempty_bar + 2;   // [4] tail-split exchange: one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xchg_bar + 4);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::BAR_BYTES);
+  uint64_t* xchg_bar = tempty_bar + 2;   // [GEMM_EPI_WARPS] tail-split exchange: one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xchg_bar + GEMM_EPI_WARPS);
+  uint8_t* epi_stage = (smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,9 +93,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&xchg_bar[s], 1);
+    for (int s = 0; s < GEMM_EPI_WARPS; ++s) mbar_init(&xchg_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -171,8 +170,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // ------------------------------------------------------------ epilogue: 8 warps; warp e drains TMEM lane quarter e % 4,
+    // 32-column chunks h, h + 2, h + 4, ... with h = e / 4 (see gemm_epilogue_chunk)
+    const int e = warp - 4;
+    const int q = e & 3, h = e >> 2;
+    uint8_t* stg = epi_stage + e * (32 * GEMM_EPI_PITCH);
+    constexpr int NCH = BLOCK_N / 32;
     uint32_t it = 0;
     GemmSchedule sched(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
     GemmSeg sg;
@@ -185,83 +188,77 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const int n0 = n_tile * BLOCK_N;
-      // Each chunk of 32 accumulator columns goes TMEM -> registers (thread = row) -> a padded shared-memory tile ->
-      // registers again with (8 rows x 4 column-pieces) per warp instruction, so that global stores and residual loads
-      // touch whole 32-byte sectors (64 B of bf16 per row) instead of one 16-byte piece of 32 different rows.
-      float* stg = epi_stage + q * (32 * Cfg::EPI_PITCH);
       if (sg.kind == 1) {
         if constexpr (HALVES == 1) {
-          // ---- tail tile: exchange partial accumulators with the other k-slices of this tile (CTAs base .. base + S - 1)
-          constexpr int NCH = BLOCK_N / 32;
+          // ---- tail tile: exchange partial accumulators with the other k-slices of this tile (CTAs base .. base + S - 1).
+          // This warp's chunks are c = h + 2 j; slice (j % S) finishes chunk j, the others publish their partial of it.
           const int S = p.tail_slices, slice = cta % S, base = cta - slice;
+          const int NL = (NCH - h + 1) / 2;                                          // chunks of this warp
           const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
           const int row_base = m_tile * BLOCK_M + q * 32;
-          // a slot is [quarter q][chunk c][row][32 floats]: 4 KB blocks, 16-byte pieces XOR-swizzled by (row % 8) so that the
-          // owner's thread-per-row reads of the block from shared memory are bank-conflict free
-          auto block_of = [&](int cta_id, int c) { return p.sk_partials + (static_cast<long long>(cta_id) * 4 + q) * (NCH * 1024) + c * 1024; };
-          // pass 1: publish the chunks other slices finish
+          // a slot is [epilogue warp][chunk j][row][32 floats]: 4 KB blocks, 16-byte pieces XOR-swizzled by (row % 8) so that the
+          // finisher's thread-per-row reads of the block from shared memory are bank-conflict free
+          auto block_of = [&](int cta_id, int j) { return p.sk_partials + ((static_cast<long long>(cta_id) * GEMM_EPI_WARPS + e) * 4 + j) * 1024; };
 #pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            if (c % S == slice) continue;
+          for (int j = 0; j < NL; ++j) {
+            if (j % S == slice) continue;
             uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_32x32(taddr + (h + 2 * j) * 32, r);
             tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(block_of(cta, c) + lane * 32);
+            float4* dst = reinterpret_cast<float4*>(block_of(cta, j) + lane * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            for (int t = 0; t < 8; ++t)
+              dst[t ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * t]), __uint_as_float(r[4 * t + 1]), __uint_as_float(r[4 * t + 2]), __uint_as_float(r[4 * t + 3]));
           }
           __threadfence();            // every lane's partial stores are visible device-wide before the flag
           __syncwarp();
-          // the tail item is the last work of the CTA: the operand ring is idle, 48 KB of it per epilogue warp receive the peers' blocks
-          float* xbuf = reinterpret_cast<float*>(smem + q * (48 * 1024));
+          // the tail item is the last work of the CTA: the operand ring is idle, 24 KB of it per epilogue warp receive the peers' blocks
+          float* xbuf = reinterpret_cast<float*>(smem + e * (24 * 1024));
           if (lane == 0) {
-            sk_flag_publish(p.sk_flags + cta * 4 + q, p.sk_epoch);
+            sk_flag_publish(p.sk_flags + cta * GEMM_EPI_WARPS + e, p.sk_epoch);
             for (int j = 0; j < S; ++j)
-              if (j != slice) sk_flag_wait(p.sk_flags + (base + j) * 4 + q, p.sk_epoch);
+              if (j != slice) sk_flag_wait(p.sk_flags + (base + j) * GEMM_EPI_WARPS + e, p.sk_epoch);
             fence_proxy_async_global();   // peers' generic-proxy stores (acquired above) -> visible to the bulk-copy engine
             uint32_t blocks = 0;
-            for (int c = slice; c < NCH; c += S) blocks += static_cast<uint32_t>(S - 1);
-            mbar_arrive_expect_tx(&xchg_bar[q], blocks * 4096u);
+            for (int j = slice; j < NL; j += S) blocks += static_cast<uint32_t>(S - 1);
+            mbar_arrive_expect_tx(&xchg_bar[e], blocks * 4096u);
             uint32_t slot = 0;
-            for (int c = slice; c < NCH; c += S)
-              for (int j = 0; j < S; ++j)
-                if (j != slice) bulk_load_1d(xbuf + (slot++) * 1024, block_of(base + j, c), 4096u, &xchg_bar[q]);
+            for (int j = slice; j < NL; j += S)
+              for (int s2 = 0; s2 < S; ++s2)
+                if (s2 != slice) bulk_load_1d(xbuf + (slot++) * 1024, block_of(base + s2, j), 4096u, &xchg_bar[e]);
           }
           __syncwarp();
-          mbar_wait(&xchg_bar[q], 0);
-          // pass 2: finish this slice's chunks: sum in slice order (own accumulator at position `slice`), then the epilogue
+          mbar_wait(&xchg_bar[e], 0);
+          // finish this slice's chunks: sum in slice order (own accumulator at position `slice`), then the epilogue
           uint32_t slot = 0;
 #pragma unroll 1
-          for (int c = slice; c < NCH; c += S) {
+          for (int j = slice; j < NL; j += S) {
+            const int c = h + 2 * j;
+            uint4 rsd[4];
+            gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
             uint32_t r[32];
             tmem_ld_32x32(taddr + c * 32, r);
             tmem_ld_wait();
             float accv[32];
             bool first = true;
-            for (int j = 0; j < S; ++j) {
-              if (j == slice) {
+            for (int s2 = 0; s2 < S; ++s2) {
+              if (s2 == slice) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) accv[e] = first ? __uint_as_float(r[e]) : accv[e] + __uint_as_float(r[e]);
+                for (int t = 0; t < 32; ++t) accv[t] = first ? __uint_as_float(r[t]) : accv[t] + __uint_as_float(r[t]);
               } else {
                 const float4* src = reinterpret_cast<const float4*>(xbuf + (slot++) * 1024 + lane * 32);
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float4 v = src[jj ^ (lane & 7)];
-                  accv[4 * jj] = first ? v.x : accv[4 * jj] + v.x;
-                  accv[4 * jj + 1] = first ? v.y : accv[4 * jj + 1] + v.y;
-                  accv[4 * jj + 2] = first ? v.z : accv[4 * jj + 2] + v.z;
-                  accv[4 * jj + 3] = first ? v.w : accv[4 * jj + 3] + v.w;
+                for (int t = 0; t < 8; ++t) {
+                  const float4 v = src[t ^ (lane & 7)];
+                  accv[4 * t] = first ? v.x : accv[4 * t] + v.x;
+                  accv[4 * t + 1] = first ? v.y : accv[4 * t + 1] + v.y;
+                  accv[4 * t + 2] = first ? v.z : accv[4 * t + 2] + v.z;
+                  accv[4 * t + 3] = first ? v.w : accv[4 * t + 3] + v.w;
                 }
               }
               first = false;
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + j * 4) = make_float4(accv[4 * j], accv[4 * j + 1], accv[4 * j + 2], accv[4 * j + 3]);
-            __syncwarp();
-            gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
-            __syncwarp();
+            gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
           }
           tc_fence_before();
           __syncwarp();
@@ -274,22 +271,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row_base = m_tile * BLOCK_M + hf * 128 + q * 32;
         const uint32_t taddr = tmem_base + (acc * HALVES + hf) * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = h; c < NCH; c += 2) {
+          uint4 rsd[4];
+          gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (hf == HALVES - 1 && c == BLOCK_N / 32 - 1) {
-            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          if (hf == HALVES - 1 && c + 2 >= NCH) {
+            // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+          float accv[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
-          __syncwarp();
+          for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
+          gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
         }
       }
     }
@@ -374,7 +371,7 @@ static void fill_kparams(const slam_gemm_args* g, int block_m, int block_n, Gemm
   p.sk_flags = nullptr;
 }
 
-constexpr int64_t SK_FLAG_BYTES = 4096;                       // [SMs][4] u32 flags at the head of the workspace
+constexpr int64_t SK_FLAG_BYTES = 8192;                       // [SMs][GEMM_EPI_WARPS] u32 flags at the head of the workspace
 static int64_t sk_workspace_bytes() { return SK_FLAG_BYTES + static_cast<int64_t>(num_sms()) * 128 * 256 * 4; }
 
 // Tail-split plan for 128-row tiles: with T tiles on G = #SMs CTAs the last wave has R = T mod G tiles; cutting each into
@@ -389,9 +386,9 @@ static void plan_tail_split(const slam_gemm_args* g, GemmKParams& p, int block_m
   const int R = T % G;
   if (R == 0) return;
   int s = G / R;
-  int max_slices = g->tail_split > 1 ? g->tail_split : 8;
-  if (max_slices > 8) max_slices = 8;                   // the exchange buffers (48 KB per epilogue warp) hold ceil(NCH / s) * (s - 1) <= 12 blocks
-  if (max_slices > block_n / 32) max_slices = block_n / 32;
+  int max_slices = g->tail_split > 1 ? g->tail_split : 4;
+  if (max_slices > 4) max_slices = 4;                   // an epilogue warp owns <= 4 chunks; its 24 KB exchange buffer holds 6 blocks
+  if (max_slices > block_n / 64) max_slices = block_n / 64;
   if (s > max_slices) s = max_slices;
   if (s > nkb / 4) s = nkb / 4;              // at least 4 k-blocks per slice
   if (s < 2) return;
@@ -538,8 +535,8 @@ static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair) {
     double tail = rem == 0 ? 0.0 : 1.0;
     if (!c.pair && tail_split && rem > 0) {
       int64_t sl = units / rem;
-      if (sl > 8) sl = 8;
-      if (sl > c.bn / 32) sl = c.bn / 32;
+      if (sl > 4) sl = 4;
+      if (sl > c.bn / 64) sl = c.bn / 64;
       if (sl > nkb / 4) sl = nkb / 4;
       if (sl >= 2) tail = 1.0 / static_cast<double>(sl) + 0.2;
     }

@@ -10,7 +10,7 @@
 //              complete_tx on it (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address);
 //   empty[s]   in each CTA; tcgen05.commit.cta_group::2 multicast from the leader frees the slot in both CTAs;
 //   tfull[a]   in each CTA; multicast commit publishes the accumulator to both epilogues;
-//   tempty[a]  leader only; 8 arrivals = 4 epilogue warps of each CTA (the peer arrives remotely through the cluster window).
+//   tempty[a]  leader only; 16 arrivals = 8 epilogue warps of each CTA (the peer arrives remotely through the cluster window).
 #pragma once
 #include "gemm_common.cuh"
 
@@ -27,7 +27,7 @@ struct GemmPairCfg {
   static constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_BYTES = 4 * 32 * GEMM_EPI_PITCH * 4;
+  static constexpr int EPI_BYTES = GEMM_EPI_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert((BLOCK_N / 2) % 8 == 0 && BLOCK_N % 16 == 0, "B half must be whole 8-row swizzle groups");
@@ -49,7 +49,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,7 +72,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -152,8 +152,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (both CTAs, each drains its own 128 rows)
-    const int q = warp - 4;
+    // ------------------------------------------------------------ epilogue (both CTAs, each drains its own 128 rows; 8 warps)
+    const int e = warp - 4;
+    const int q = e & 3, h = e >> 2;
+    uint8_t* stg = epi_stage + e * (32 * GEMM_EPI_PITCH);
+    constexpr int NCH = BLOCK_N / 32;
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint32_t it = 0;
     for (int item = pair; item < total_items; item += npairs, ++it) {
@@ -165,25 +168,24 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const int n0 = n_tile * BLOCK_N;
-      float* stg = epi_stage + q * (32 * GEMM_EPI_PITCH);
       const int row_base = m_tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = h; c < NCH; c += 2) {
+        uint4 rsd[4];
+        gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {
+        if (c + 2 >= NCH) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(tempty_leader0 + acc * 8);
         }
+        float accv[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * GEMM_EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        gemm_epilogue_store_chunk(p, stg, row_base, n0 + c * 32, lane);
-        __syncwarp();
+        for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
+        gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
       }
     }
   }

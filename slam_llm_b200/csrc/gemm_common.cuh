@@ -5,16 +5,18 @@
 namespace slam {
 
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_EPI_PITCH = 36;                                    // floats per staged row (32 + 4 pad: conflict-free)
+constexpr int GEMM_EPI_WARPS = 8;                                     // two warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;               // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4.. epilogue
+constexpr int GEMM_EPI_PITCH = 80;                                    // bytes per staged bf16 row (64 + 16 pad: conflict-free)
+constexpr int GEMM_EPI_BYTES = GEMM_EPI_WARPS * 32 * GEMM_EPI_PITCH;  // one 32 x 32 bf16 chunk per epilogue warp
 
 struct GemmKParams {
   int M, N;
   int kb1, kb2;
   int ksplit, kb_per_split;   // split-K: work item = (tile, k-slice); partial tiles are merged with fp32 atomics
   int tail_tiles, tail_slices, tail_kb;   // tail split: the last tail_tiles tiles are cut into tail_slices k-slices of tail_kb k-blocks
-  float* sk_partials;         // [gridDim.x] slots of 128 x BLOCK_N fp32, laid out [warp quarter][chunk][row][32 cols, 16-B pieces swizzled]
-  unsigned int* sk_flags;     // [gridDim.x][4] flag = epoch of the launch whose partial (of epilogue warp q) is published
+  float* sk_partials;         // [gridDim.x] slots of 128 x 256 fp32, laid out [epilogue warp][its chunk j][row][32 cols, 16-B pieces swizzled]
+  unsigned int* sk_flags;     // [gridDim.x][8] flag = epoch of the launch whose partial (of epilogue warp e) is published
   unsigned int sk_epoch;      // distinct per launch, never 0
   int num_m_tiles, num_n_tiles;
   void* out;
@@ -100,57 +102,87 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Epilogue tail shared by both kernels: one warp has staged a 32 x 32 fp32 chunk of the accumulator (thread = row) in a padded
-// shared-memory tile; it is read back as (8 rows x 4 column-pieces) per warp instruction so that global stores and residual
-// loads touch whole 32-byte sectors, then alpha / bias / activation / residual are applied and 16-byte stores issued.
-__device__ __forceinline__ void gemm_epilogue_store_chunk(const GemmKParams& p, const float* stg, int row_base, int col0, int lane) {
+// Epilogue of one 32-column chunk, shared by both kernels.  Measured on B200 (tools/epi_probe.py) the round-1 epilogue - 4 warps,
+// fp32 staging, residual loaded after the transpose - took 7.7 us per 128 x 256 tile plain, 14 us with bias + GELU and 23 us with
+// a residual: more than the MMA time of a K = 1280 tile (6 us), i.e. the Whisper GEMMs were epilogue-bound.  Now: 8 epilogue
+// warps; all math happens in the TMEM register layout (thread = row, 32 consecutive columns), with the row's residual (64
+// contiguous bytes = two full sectors) requested BEFORE the TMEM load so its latency overlaps; only the packed bf16 result is
+// transposed through a padded shared-memory tile so that a warp store instruction covers 8 rows x 64 B of whole sectors.
+__device__ __forceinline__ void gemm_residual_prefetch(const GemmKParams& p, int row, int col0, uint4 (&rsd)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) rsd[g] = make_uint4(0u, 0u, 0u, 0u);
+  if (p.residual != nullptr && row < p.M) {
+    const bf16* src = p.residual + static_cast<long long>(row) * p.ldr + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (col0 + 8 * g < p.N) rsd[g] = *reinterpret_cast<const uint4*>(src + 8 * g);
+  }
+}
+
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const float (&acc)[32], const uint4 (&rsd)[4], int row_base, int col0,
+                                                    uint8_t* stg, int lane) {
+  const int row = row_base + lane;
+  float v[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = acc[e] * p.alpha;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (col0 + 4 * g < p.N) {                                   // (N is a multiple of 8: a float4 never straddles the edge)
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * g));   // same address in every lane: one broadcast
+        v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+      }
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+  }
+  if (p.residual != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float2 r0 = unpack_bf16x2(rsd[g].x), r1 = unpack_bf16x2(rsd[g].y), r2 = unpack_bf16x2(rsd[g].z), r3 = unpack_bf16x2(rsd[g].w);
+      v[8 * g] += r0.x; v[8 * g + 1] += r0.y; v[8 * g + 2] += r1.x; v[8 * g + 3] += r1.y;
+      v[8 * g + 4] += r2.x; v[8 * g + 5] += r2.y; v[8 * g + 6] += r3.x; v[8 * g + 7] += r3.y;
+    }
+  }
+  if (p.ksplit > 1) {                                             // k-slices merge into the zero-initialised fp32 output
+    if (row < p.M) {
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (col0 + e < p.N) atomicAdd(o + e, v[e]);
+    }
+    return;
+  }
+  if (p.out_f32) {                                                // fp32 outputs (logits, thin products) go out in the row layout
+    if (row < p.M) {
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (col0 + 4 * g < p.N) *reinterpret_cast<float4*>(o + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stg + lane * GEMM_EPI_PITCH + 16 * g) =
+        make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]), pack_bf16x2(v[8 * g + 4], v[8 * g + 5]),
+                   pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+  __syncwarp();
   const int piece = lane & 3;
   const int col = col0 + piece * 8;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = i * 8 + (lane >> 2);
-    const int row = row_base + rr;
-    if (row >= p.M || col >= p.N) continue;
-    const float4 x0 = *reinterpret_cast<const float4*>(stg + rr * GEMM_EPI_PITCH + piece * 8);
-    const float4 x1 = *reinterpret_cast<const float4*>(stg + rr * GEMM_EPI_PITCH + piece * 8 + 4);
-    float v[8] = {x0.x * p.alpha, x0.y * p.alpha, x0.z * p.alpha, x0.w * p.alpha, x1.x * p.alpha, x1.y * p.alpha, x1.z * p.alpha, x1.w * p.alpha};
-    if (p.bias != nullptr) {
-      const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    if (p.act == 1) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-    } else if (p.act == 2) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-    }
-    if (p.residual != nullptr) {
-      const uint4 rsd = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-      const float2 r0 = unpack_bf16x2(rsd.x), r1 = unpack_bf16x2(rsd.y), r2 = unpack_bf16x2(rsd.z), r3 = unpack_bf16x2(rsd.w);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-      v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-    }
-    if (p.ksplit > 1) {
-      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(o + e, v[e]);      // k-slices merge into the zero-initialised fp32 output
-    } else if (p.out_f32) {
-      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-      uint4 pk;
-      pk.x = pack_bf16x2(v[0], v[1]);
-      pk.y = pack_bf16x2(v[2], v[3]);
-      pk.z = pack_bf16x2(v[4], v[5]);
-      pk.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(o) = pk;
-    }
+    const uint4 pk = *reinterpret_cast<const uint4*>(stg + rr * GEMM_EPI_PITCH + piece * 16);
+    if (row_base + rr < p.M && col < p.N)
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row_base + rr) * p.ldo + col) = pk;
   }
+  __syncwarp();
 }
 
 }  // namespace slam
