@@ -440,6 +440,177 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restr
   }
 }
 
+// ---------------------------------------------------------------- register-resident norms for the common hidden sizes
+// One row = TPR threads, each holding NV 16-byte vectors of the row in registers: every operand is read from memory exactly
+// once, and a 1604 x 4096 activation still spreads over 6416 warps (the warp-per-row kernels above leave the GPU at ~11 warps
+// per SM for that shape and re-read the row from L1 for every pass: 26 us for rmsnorm_bwd against ~6 us of memory time).
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  if constexpr (TPR > 32) {
+    constexpr int WPR = TPR / 32;
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();                                  // s_red may still be read from a previous reduction
+    if ((threadIdx.x & 31) == 0) s_red[warp] = v;
+    __syncthreads();
+    const int first = (warp / WPR) * WPR;
+    v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) v += s_red[first + i];
+  }
+  return v;
+}
+
+template <int NV, int TPR>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_reg_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                              float* __restrict__ rstd_out, int rows, float eps) {
+  constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
+  __shared__ float s_red[8];
+  pdl_trigger();
+  const int t = threadIdx.x % TPR;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * RPC + threadIdx.x / TPR;
+  const bool ok = row < rows;
+  const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + (ok ? row : rows - 1) * D);
+  bf16x8 xv[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) xv[j] = xr[j * TPR + t];
+  float ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float v[8];
+    unpack8(xv[j], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+  }
+  ss = row_sum<TPR>(ss, s_red);
+  const float rstd = rsqrtf(ss / static_cast<float>(D) + eps);
+  if (!ok) return;
+  if (t == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+  const bf16x8* wr = reinterpret_cast<const bf16x8*>(w);
+  bf16x8* yr = reinterpret_cast<bf16x8*>(y + row * D);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float v[8], wf[8], o[8];
+    unpack8(xv[j], v);
+    unpack8(wr[j * TPR + t], wf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = v[e] * rstd * wf[e];
+    yr[j * TPR + t] = pack8(o);
+  }
+}
+
+template <int NV, int TPR>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_reg_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                              const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
+                                                              bf16* __restrict__ dx, int rows) {
+  constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
+  __shared__ float s_red[8];
+  pdl_trigger();
+  const int t = threadIdx.x % TPR;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * RPC + threadIdx.x / TPR;
+  const bool ok = row < rows;
+  const int64_t rc = ok ? row : rows - 1;
+  const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + rc * D);
+  const bf16x8* gr = reinterpret_cast<const bf16x8*>(dy + rc * D);
+  const bf16x8* wr = reinterpret_cast<const bf16x8*>(w);
+  bf16x8 xv[NV], gv[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    xv[j] = xr[j * TPR + t];
+    gv[j] = gr[j * TPR + t];
+  }
+  float gw[NV][8];                                    // dy * w, reused for the output
+  float dot = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float xf[8], gf[8], wf[8];
+    unpack8(xv[j], xf);
+    unpack8(gv[j], gf);
+    unpack8(wr[j * TPR + t], wf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gw[j][e] = gf[e] * wf[e];
+      dot += gw[j][e] * xf[e];
+    }
+  }
+  dot = row_sum<TPR>(dot, s_red);
+  if (!ok) return;
+  const float rstd = rstd_in[row];
+  const float coef = dot * rstd * rstd * rstd / static_cast<float>(D);
+  bf16x8* dxr = reinterpret_cast<bf16x8*>(dx + row * D);
+  const bf16x8* rr = dres != nullptr ? reinterpret_cast<const bf16x8*>(dres + row * D) : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float xf[8], o[8];
+    unpack8(xv[j], xf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = gw[j][e] * rstd - xf[e] * coef;
+    if (rr != nullptr) {
+      float rf[8];
+      unpack8(rr[j * TPR + t], rf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += rf[e];
+    }
+    dxr[j * TPR + t] = pack8(o);
+  }
+}
+
+template <int NV, int TPR>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                            bf16* __restrict__ y, int rows, float eps) {
+  constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
+  __shared__ float s_red[8];
+  pdl_trigger();
+  const int t = threadIdx.x % TPR;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * RPC + threadIdx.x / TPR;
+  const bool ok = row < rows;
+  const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + (ok ? row : rows - 1) * D);
+  float xf[NV][8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    unpack8(xr[j * TPR + t], xf[j]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += xf[j][e];
+  }
+  const float mean = row_sum<TPR>(sum, s_red) / static_cast<float>(D);
+  float ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float c = xf[j][e] - mean;
+      ss += c * c;
+    }
+  const float rstd = rsqrtf(row_sum<TPR>(ss, s_red) / static_cast<float>(D) + eps);
+  if (!ok) return;
+  bf16x8* yr = reinterpret_cast<bf16x8*>(y + row * D);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = (j * TPR + t) * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + c0), w1 = *reinterpret_cast<const float4*>(w + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(b + c0), b1 = *reinterpret_cast<const float4*>(b + c0 + 4);
+    const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (xf[j][e] - mean) * rstd * wf[e] + bf[e];
+    yr[j * TPR + t] = pack8(o);
+  }
+}
+
+// hidden sizes with a register-resident instance: d -> (NV, TPR)
+#define SLAM_NORM_DISPATCH(D_, LAUNCH)            \
+  switch (D_) {                                   \
+    case 4096: LAUNCH(4, 128); break;             \
+    case 2048: LAUNCH(4, 64); break;              \
+    case 1280: LAUNCH(5, 32); break;              \
+    case 1024: LAUNCH(4, 32); break;              \
+    case 768: LAUNCH(3, 32); break;               \
+    case 512: LAUNCH(2, 32); break;               \
+    default: break;                               \
+  }
+
 // ---------------------------------------------------------------- RoPE (HF apply_rotary_pos_emb, rotate_half; modeling_llama.py:138-168)
 // x viewed as [rows, n_heads, dh] with row stride ld; cos/sin f32 [seq_len, dh/2]; 8 pairs per thread
 __global__ void rope_kernel(bf16* __restrict__ x, int64_t ld, int rows, int seq_len, int n_heads, int dh, const float* __restrict__ cosT,
@@ -765,20 +936,40 @@ int slam_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* o
 
 int slam_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int32_t rows, int32_t d, float eps, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "rmsnorm_fwd: bad shape rows=%d d=%d", rows, d);
-  rmsnorm_fwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), CBF(w), BF(y), rstd, rows, d, eps);
+  bool done = false;
+#define SLAM_L(NV, TPR)                                                                                                                  \
+  rmsnorm_fwd_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(x), CBF(w), BF(y), rstd, rows, eps); \
+  done = true
+  SLAM_NORM_DISPATCH(d, SLAM_L)
+#undef SLAM_L
+  if (!done) rmsnorm_fwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), CBF(w), BF(y), rstd, rows, d, eps);
   SLAM_LAUNCH_CHECK("slam_rmsnorm_fwd");
   return 0;
 }
 int slam_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx, int32_t rows, int32_t d,
                      void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "rmsnorm_bwd: bad shape rows=%d d=%d", rows, d);
-  rmsnorm_bwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), rows, d);
+  bool done = false;
+#define SLAM_L(NV, TPR)                                                                                                                 \
+  rmsnorm_bwd_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), \
+                                                                                                         BF(dx), rows);                \
+  done = true
+  SLAM_NORM_DISPATCH(d, SLAM_L)
+#undef SLAM_L
+  if (!done)
+    rmsnorm_bwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), rows, d);
   SLAM_LAUNCH_CHECK("slam_rmsnorm_bwd");
   return 0;
 }
 int slam_layernorm(const void* x, const float* w, const float* b, void* y, int32_t rows, int32_t d, float eps, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "layernorm: bad shape rows=%d d=%d", rows, d);
-  layernorm_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), w, b, BF(y), rows, d, eps);
+  bool done = false;
+#define SLAM_L(NV, TPR)                                                                                                       \
+  layernorm_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(x), w, b, BF(y), rows, eps); \
+  done = true
+  SLAM_NORM_DISPATCH(d, SLAM_L)
+#undef SLAM_L
+  if (!done) layernorm_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), w, b, BF(y), rows, d, eps);
   SLAM_LAUNCH_CHECK("slam_layernorm");
   return 0;
 }

@@ -226,7 +226,7 @@ def test_conv_stem_im2col(ops):
     assert rel_err(y3, y2.view(B, 100, Cout).float() + pos[:100]) < 1e-2
 
 
-@pytest.mark.parametrize("d", [384, 512, 1280])
+@pytest.mark.parametrize("d", [384, 512, 768, 1024, 1280])
 def test_layernorm(ops, d):
     x = rnd(777, d, scale=2.0, seed=24)
     w, b = rnd(d, dtype=F32, seed=25), rnd(d, dtype=F32, seed=26)
@@ -348,7 +348,7 @@ def test_embed_merge(ops):
 
 
 # ----------------------------------------------------------------------------------------------- decoder element-wise
-@pytest.mark.parametrize("d", [2048, 4096, 896])
+@pytest.mark.parametrize("d", [2048, 4096, 896, 1024, 512])
 def test_rmsnorm(ops, d):
     x, w = rnd(333, d, scale=3.0, seed=32), (rnd(d, seed=33) * 0.1 + 1.0).to(BF16)
     y, rstd = ops.rmsnorm_fwd(x, w, 1e-5)
