@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SLAM_B200_ABI_VERSION 2
+#define SLAM_B200_ABI_VERSION 3
 
 int slam_abi_version(void);
 const char* slam_last_error(void);
@@ -49,7 +49,7 @@ typedef struct slam_gemm_args {
   const void* b2;  int64_t ldb2;  /* bf16 [N,K2] */
   void* out;       int64_t ldo;   /* bf16 or f32 [M,N] */
   int32_t out_f32;                /* 0: bf16 out, 1: f32 out */
-  int32_t act;                    /* 0 none, 1 GELU(erf), 2 ReLU */
+  int32_t act;                    /* 0 none, 1 GELU(erf), 2 ReLU, 3 SwiGLU forward, 4 SwiGLU backward (see `aux`) */
   const float* bias;              /* f32 [N] or NULL */
   const void* residual; int64_t ldr; /* bf16 [M,N] or NULL; added after activation */
   float alpha;
@@ -69,6 +69,14 @@ typedef struct slam_gemm_args {
   int64_t workspace_bytes;
   int32_t tail_split;             /* 0 = automatic (when a workspace is given), -1 = never, n > 1 = at most n k-slices per tile */
   int32_t reserved;
+  void* aux; int64_t ld_aux;      /* fused SwiGLU (HF LlamaMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x)), modeling_llama.py), with the
+                                     gate/up pair stored "blocked-64": feature 64 b + i has its gate in column 128 b + i and its up in
+                                     column 128 b + 64 + i of a [M, 2F] matrix (weights pre-permuted by the caller to match).
+                                     act 3: out = gu [M, N = 2F] as usual, and aux (bf16 [M, F], written) = silu(gate) * up computed from
+                                            the bf16-rounded gu - identical to slam_swiglu_fwd on `out`;
+                                     act 4: the product is dh [M, N = F] (never stored); aux (bf16 [M, 2F], read) = gu, and
+                                            out (bf16 [M, 2F]) = d(gu) - identical to slam_swiglu_bwd(gu, bf16(dh)).
+                                     Both need bf16 out, no bias / residual / split_k; act 3 needs tiles of 128 or 256 columns */
 } slam_gemm_args;
 int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
 /* bytes of `workspace` the tail split needs on the current device (SM count x one 128 x 256 fp32 tile + flags) */
@@ -156,9 +164,10 @@ int slam_rmsnorm_bwd(const void* dy_bf16, const void* x_bf16, const void* w_bf16
  * LlamaRotaryEmbedding); inverse != 0 applies the transpose rotation (backward). */
 int slam_rope(void* x_bf16, int64_t ld, int32_t rows, int32_t seq_len, int32_t n_heads, int32_t dh,
               const float* cos_table, const float* sin_table, int32_t inverse, void* stream);
-/* h = silu(g) * u with gu = [g | u] bf16 [rows, 2F] */
-int slam_swiglu_fwd(const void* gu_bf16, void* h_bf16, int32_t rows, int32_t f, void* stream);
-int slam_swiglu_bwd(const void* gu_bf16, const void* dh_bf16, void* dgu_bf16, int32_t rows, int32_t f,
+/* h = silu(g) * u with gu bf16 [rows, 2F]; block = 0: gu = [g | u] (HF order of the concatenated gate/up weight);
+ * block = 64: "blocked-64" order (see slam_gemm_args.aux), used when the fused GEMM epilogues are not */
+int slam_swiglu_fwd(const void* gu_bf16, void* h_bf16, int32_t rows, int32_t f, int32_t block, void* stream);
+int slam_swiglu_bwd(const void* gu_bf16, const void* dh_bf16, void* dgu_bf16, int32_t rows, int32_t f, int32_t block,
                     void* stream);
 
 /* a6  LoRA-branch dropout (peft lora.Linear.forward: lora_B(lora_A(dropout(x))) — train_config.peft_config.lora_dropout).

@@ -646,7 +646,17 @@ __global__ void rope_kernel(bf16* __restrict__ x, int64_t ld, int rows, int seq_
 }
 
 // ---------------------------------------------------------------- SwiGLU (HF LlamaMLP; modeling_llama.py:182-184)
-__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, int rows, int f) {
+// column of the gate of feature c (a multiple of 8) inside a [rows, 2F] gate/up matrix, and the distance to its up partner
+__device__ __forceinline__ void swiglu_cols(int c, int f, int block, int& gcol, int& udist) {
+  if (block == 0) {
+    gcol = c;
+    udist = f;
+  } else {                                           // blocked: [block gates | block ups] per group of `block` features
+    gcol = (c / block) * 2 * block + (c % block);
+    udist = block;
+  }
+}
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, int rows, int f, int block) {
   pdl_trigger();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
@@ -656,14 +666,16 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
     const int64_t r = i / vpr;
     const int c = static_cast<int>(i % vpr) * 8;
     float g[8], u[8], o[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + c), g);
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + f + c), u);
+    int gcol, udist;
+    swiglu_cols(c, f, block, gcol, udist);
+    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + gcol), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + gcol + udist), u);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = g[e] / (1.0f + expf(-g[e])) * u[e];
     *reinterpret_cast<bf16x8*>(h + r * f + c) = pack8(o);
   }
 }
-__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dh, bf16* __restrict__ dgu, int rows, int f) {
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dh, bf16* __restrict__ dgu, int rows, int f, int block) {
   pdl_trigger();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
@@ -673,8 +685,10 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
     const int64_t r = i / vpr;
     const int c = static_cast<int>(i % vpr) * 8;
     float g[8], u[8], d[8], dg[8], du[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + c), g);
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + f + c), u);
+    int gcol, udist;
+    swiglu_cols(c, f, block, gcol, udist);
+    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + gcol), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(gu + r * 2 * f + gcol + udist), u);
     unpack8(*reinterpret_cast<const bf16x8*>(dh + r * f + c), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -683,8 +697,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
       du[e] = d[e] * silu;
       dg[e] = d[e] * u[e] * sg * (1.0f + g[e] * (1.0f - sg));
     }
-    *reinterpret_cast<bf16x8*>(dgu + r * 2 * f + c) = pack8(dg);
-    *reinterpret_cast<bf16x8*>(dgu + r * 2 * f + f + c) = pack8(du);
+    *reinterpret_cast<bf16x8*>(dgu + r * 2 * f + gcol) = pack8(dg);
+    *reinterpret_cast<bf16x8*>(dgu + r * 2 * f + gcol + udist) = pack8(du);
   }
 }
 
@@ -981,15 +995,15 @@ int slam_rope(void* x, int64_t ld, int32_t rows, int32_t seq_len, int32_t n_head
   SLAM_LAUNCH_CHECK("slam_rope");
   return 0;
 }
-int slam_swiglu_fwd(const void* gu, void* h, int32_t rows, int32_t f, void* stream) {
-  SLAM_CHECK_ARG(f % 8 == 0, "swiglu: f %% 8 != 0");
-  swiglu_fwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), BF(h), rows, f);
+int slam_swiglu_fwd(const void* gu, void* h, int32_t rows, int32_t f, int32_t block, void* stream) {
+  SLAM_CHECK_ARG(f % 8 == 0 && (block == 0 || (block % 8 == 0 && f % block == 0)), "swiglu: f %% 8 != 0 or bad block");
+  swiglu_fwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), BF(h), rows, f, block);
   SLAM_LAUNCH_CHECK("slam_swiglu_fwd");
   return 0;
 }
-int slam_swiglu_bwd(const void* gu, const void* dh, void* dgu, int32_t rows, int32_t f, void* stream) {
-  SLAM_CHECK_ARG(f % 8 == 0, "swiglu: f %% 8 != 0");
-  swiglu_bwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), CBF(dh), BF(dgu), rows, f);
+int slam_swiglu_bwd(const void* gu, const void* dh, void* dgu, int32_t rows, int32_t f, int32_t block, void* stream) {
+  SLAM_CHECK_ARG(f % 8 == 0 && (block == 0 || (block % 8 == 0 && f % block == 0)), "swiglu: f %% 8 != 0 or bad block");
+  swiglu_bwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), CBF(dh), BF(dgu), rows, f, block);
   SLAM_LAUNCH_CHECK("slam_swiglu_bwd");
   return 0;
 }

@@ -270,23 +270,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int hf = 0; hf < HALVES; ++hf) {
         const int row_base = m_tile * BLOCK_M + hf * 128 + q * 32;
         const uint32_t taddr = tmem_base + (acc * HALVES + hf) * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+        auto release_tmem = [&]() {   // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        };
+        if (p.act == 3) {
+          // fused SwiGLU forward: in the blocked-64 layout chunk 4b + h is a gate chunk and 4b + h + 2 its up partner
+          if constexpr (BLOCK_N % 128 == 0) {
+#pragma unroll 1
+            for (int cg = h; cg < NCH; cg += 4) {
+              uint32_t rg[32], ru[32];
+              tmem_ld_32x32(taddr + cg * 32, rg);
+              tmem_ld_32x32(taddr + (cg + 2) * 32, ru);
+              tmem_ld_wait();
+              if (hf == HALVES - 1 && cg + 4 >= NCH) release_tmem();
+              float ag[32], au[32];
+#pragma unroll
+              for (int t = 0; t < 32; ++t) {
+                ag[t] = __uint_as_float(rg[t]);
+                au[t] = __uint_as_float(ru[t]);
+              }
+              gemm_epilogue_swiglu_fwd(p, ag, au, row_base, n0 + cg * 32, stg, lane);
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int c = h; c < NCH; c += 2) {
-          uint4 rsd[4];
-          gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
+          uint4 rsd[4], rsd2[4];
+          if (p.act == 4) gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
+          else gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (hf == HALVES - 1 && c + 2 >= NCH) {
-            // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
+          if (hf == HALVES - 1 && c + 2 >= NCH) release_tmem();
           float accv[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
-          gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
+          if (p.act == 4) gemm_epilogue_swiglu_bwd(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
+          else gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
         }
       }
     }
@@ -357,6 +380,8 @@ static void fill_kparams(const slam_gemm_args* g, int block_m, int block_n, Gemm
   p.bias = g->bias;
   p.residual = reinterpret_cast<const bf16*>(g->residual);
   p.ldr = g->ldr;
+  p.aux = reinterpret_cast<bf16*>(g->aux);
+  p.ld_aux = g->ld_aux;
   p.alpha = g->alpha;
   p.ksplit = g->split_k > 1 ? g->split_k : 1;
   const int nkb_total = p.kb1 + p.kb2;
@@ -378,7 +403,7 @@ static int64_t sk_workspace_bytes() { return SK_FLAG_BYTES + static_cast<int64_t
 // s = floor(G / R) k-slices (capped: the owner CTA reads s - 1 partial tiles back from L2) keeps R * s CTAs busy for 1/s of a
 // tile time instead of R CTAs for a whole one.
 static void plan_tail_split(const slam_gemm_args* g, GemmKParams& p, int block_m, int block_n) {
-  if (g->workspace == nullptr || g->tail_split < 0 || block_m != 128 || p.ksplit > 1) return;
+  if (g->workspace == nullptr || g->tail_split < 0 || block_m != 128 || p.ksplit > 1 || g->act >= 3) return;
   if (g->workspace_bytes < sk_workspace_bytes() || (reinterpret_cast<uintptr_t>(g->workspace) & 15) != 0) return;
   const int G = num_sms();
   const int T = p.num_m_tiles * p.num_n_tiles;
@@ -516,7 +541,7 @@ struct TileCand {
   double pen;
   bool pair;
 };
-static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair) {
+static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair, bool need_bn128, bool heavy_epilogue) {
   if (n <= 64) return 128 * 1000 + 64;
   static const TileCand cands[] = {
       {128256, 128, 256, 1.000, false}, {128192, 128, 192, 0.977, false}, {128128, 128, 128, 1.170, false},
@@ -528,6 +553,7 @@ static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair) {
   int best_code = 128256;
   for (const TileCand& c : cands) {
     if (c.pair && !allow_pair) continue;
+    if (need_bn128 && c.bn % 128 != 0) continue;                   // SwiGLU forward pairs chunks 64 columns apart
     if (c.bn >= n + 64) continue;                                  // more than two chunks of padding columns
     const int64_t tiles = ceil_div(m, c.rows) * ceil_div(n, c.bn);
     const int units = c.pair ? sms / 2 : sms;
@@ -540,7 +566,9 @@ static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair) {
       if (sl > nkb / 4) sl = nkb / 4;
       if (sl >= 2) tail = 1.0 / static_cast<double>(sl) + 0.2;
     }
-    const double cost = (static_cast<double>(full) + tail) * c.bn * c.pen;
+    // the SwiGLU-backward epilogue (two bf16 reads, two exp, two stores per output) outlasts the MMA of a 128 x 256 tile at
+    // K = 4096 on one SM; the pair kernels hide it (tools/swiglu_probe.py: 206 us vs 187 us on the d_down shape)
+    const double cost = (static_cast<double>(full) + tail) * c.bn * c.pen * (heavy_epilogue && !c.pair ? 1.15 : 1.0);
     if (cost < best) {
       best = cost;
       best_code = c.code;
@@ -566,9 +594,17 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
   SLAM_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && g->bias == nullptr && g->residual == nullptr && g->act == 0),
                  "gemm: split_k needs a zero-initialised f32 output and no bias/activation/residual");
+  SLAM_CHECK_ARG(g->act >= 0 && g->act <= 4, "gemm: unknown act %d", g->act);
+  if (g->act >= 3) {
+    SLAM_CHECK_ARG(g->aux != nullptr && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0 && g->ld_aux % 8 == 0 && !g->out_f32 &&
+                       g->bias == nullptr && g->residual == nullptr && g->split_k <= 1,
+                   "gemm: fused SwiGLU needs a 16-byte aligned aux, a bf16 output and no bias/residual/split_k");
+    SLAM_CHECK_ARG(g->act == 3 ? g->n % 128 == 0 : g->n % 64 == 0, "gemm: fused SwiGLU needs whole blocked-64 groups (n=%d)", g->n);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
-  if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1, g->split_k <= 1);
+  if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1 && g->act < 3, g->split_k <= 1, g->act == 3, g->act == 4);
+  SLAM_CHECK_ARG(g->act != 3 || (tile % 1000) % 128 == 0, "gemm: SwiGLU forward needs a tile of 128 or 256 columns (tile %d)", tile);
   if (tile < 1000) tile += 128 * 1000;   // (2000000 + BLOCK_N = CTA-pair kernel)
   switch (tile) {
     case 128256: return launch_gemm<128, 256>(g, st);

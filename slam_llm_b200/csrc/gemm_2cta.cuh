@@ -170,22 +170,46 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = n_tile * BLOCK_N;
       const int row_base = m_tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_leader0 + acc * 8);
+      };
+      if (p.act == 3) {
+        // fused SwiGLU forward: in the blocked-64 layout chunk 4b + h is a gate chunk and 4b + h + 2 its up partner
+        if constexpr (BLOCK_N % 128 == 0) {
+#pragma unroll 1
+          for (int cg = h; cg < NCH; cg += 4) {
+            uint32_t rg[32], ru[32];
+            tmem_ld_32x32(taddr + cg * 32, rg);
+            tmem_ld_32x32(taddr + (cg + 2) * 32, ru);
+            tmem_ld_wait();
+            if (cg + 4 >= NCH) release_tmem();
+            float ag[32], au[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              ag[t] = __uint_as_float(rg[t]);
+              au[t] = __uint_as_float(ru[t]);
+            }
+            gemm_epilogue_swiglu_fwd(p, ag, au, row_base, n0 + cg * 32, stg, lane);
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = h; c < NCH; c += 2) {
-        uint4 rsd[4];
-        gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
+        uint4 rsd[4], rsd2[4];
+        if (p.act == 4) gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
+        else gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c + 2 >= NCH) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(tempty_leader0 + acc * 8);
-        }
+        if (c + 2 >= NCH) release_tmem();
         float accv[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
-        gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
+        if (p.act == 4) gemm_epilogue_swiglu_bwd(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
+        else gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
       }
     }
   }

@@ -26,6 +26,8 @@ struct GemmKParams {
   const float* bias;
   const bf16* residual;
   long long ldr;
+  bf16* aux;                  // fused SwiGLU: act 3 -> h [M, N/2] (written); act 4 -> gu [M, 2N] (read)
+  long long ld_aux;
   float alpha;
 };
 
@@ -108,6 +110,25 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // warps; all math happens in the TMEM register layout (thread = row, 32 consecutive columns), with the row's residual (64
 // contiguous bytes = two full sectors) requested BEFORE the TMEM load so its latency overlaps; only the packed bf16 result is
 // transposed through a padded shared-memory tile so that a warp store instruction covers 8 rows x 64 B of whole sectors.
+// one warp's 32 x 32 bf16 chunk (thread = row, 16 packed pairs) -> padded shared-memory tile -> 16-byte global stores that
+// cover 8 rows x 64 B of whole sectors per instruction
+__device__ __forceinline__ void gemm_store_chunk_bf16(bf16* out, long long ldo, int M, int N, const uint32_t (&pk)[16], int row_base, int col0,
+                                                      uint8_t* stg, int lane) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stg + lane * GEMM_EPI_PITCH + 16 * g) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+  __syncwarp();
+  const int piece = lane & 3;
+  const int col = col0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2);
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * GEMM_EPI_PITCH + piece * 16);
+    if (row_base + rr < M && col < N) *reinterpret_cast<uint4*>(out + static_cast<long long>(row_base + rr) * ldo + col) = v;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void gemm_residual_prefetch(const GemmKParams& p, int row, int col0, uint4 (&rsd)[4]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) rsd[g] = make_uint4(0u, 0u, 0u, 0u);
@@ -167,22 +188,70 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
     }
     return;
   }
+  uint32_t pk[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<uint4*>(stg + lane * GEMM_EPI_PITCH + 16 * g) =
-        make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]), pack_bf16x2(v[8 * g + 4], v[8 * g + 5]),
-                   pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-  __syncwarp();
-  const int piece = lane & 3;
-  const int col = col0 + piece * 8;
+  for (int t = 0; t < 16; ++t) pk[t] = pack_bf16x2(v[2 * t], v[2 * t + 1]);
+  gemm_store_chunk_bf16(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, p.N, pk, row_base, col0, stg, lane);
+}
+
+// SwiGLU math on bf16-rounded values, exactly as slam_swiglu_fwd / slam_swiglu_bwd compute it (elementwise.cu)
+__device__ __forceinline__ float swiglu_fwd_elem(float g, float u) { return g / (1.0f + expf(-g)) * u; }
+__device__ __forceinline__ void swiglu_bwd_elem(float g, float u, float d, float& dg, float& du) {
+  const float sg = 1.0f / (1.0f + expf(-g));
+  du = d * (g * sg);
+  dg = d * u * sg * (1.0f + g * (1.0f - sg));
+}
+
+// act 3: the thread holds the accumulators of a gate chunk and of its up partner (64 columns further in the blocked-64 layout).
+// Writes both chunks of gu and the chunk of h = silu(g) * u.  col_g = global (blocked) column of the gate chunk.
+__device__ __forceinline__ void gemm_epilogue_swiglu_fwd(const GemmKParams& p, const float (&ag)[32], const float (&au)[32], int row_base, int col_g,
+                                                         uint8_t* stg, int lane) {
+  uint32_t pg[16], pu[16], ph[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = i * 8 + (lane >> 2);
-    const uint4 pk = *reinterpret_cast<const uint4*>(stg + rr * GEMM_EPI_PITCH + piece * 16);
-    if (row_base + rr < p.M && col < p.N)
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row_base + rr) * p.ldo + col) = pk;
+  for (int t = 0; t < 16; ++t) {
+    pg[t] = pack_bf16x2(ag[2 * t] * p.alpha, ag[2 * t + 1] * p.alpha);
+    pu[t] = pack_bf16x2(au[2 * t] * p.alpha, au[2 * t + 1] * p.alpha);
+    const float2 g = unpack_bf16x2(pg[t]), u = unpack_bf16x2(pu[t]);
+    ph[t] = pack_bf16x2(swiglu_fwd_elem(g.x, u.x), swiglu_fwd_elem(g.y, u.y));
   }
-  __syncwarp();
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  gemm_store_chunk_bf16(out, p.ldo, p.M, p.N, pg, row_base, col_g, stg, lane);
+  gemm_store_chunk_bf16(out, p.ldo, p.M, p.N, pu, row_base, col_g + 64, stg, lane);
+  gemm_store_chunk_bf16(p.aux, p.ld_aux, p.M, p.N / 2, ph, row_base, (col_g >> 7) * 64 + (col_g & 127), stg, lane);
+}
+
+// act 4: the accumulator chunk is dh for 32 features starting at f0; rg / ru = this row's gate / up values (prefetched from gu).
+__device__ __forceinline__ void gemm_swiglu_bwd_prefetch(const GemmKParams& p, int row, int f0, uint4 (&rg)[4], uint4 (&ru)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) rg[g] = ru[g] = make_uint4(0u, 0u, 0u, 0u);
+  if (row < p.M && f0 < p.N) {
+    const bf16* src = p.aux + static_cast<long long>(row) * p.ld_aux + (f0 >> 6) * 128 + (f0 & 63);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      rg[g] = *reinterpret_cast<const uint4*>(src + 8 * g);
+      ru[g] = *reinterpret_cast<const uint4*>(src + 64 + 8 * g);
+    }
+  }
+}
+__device__ __forceinline__ void gemm_epilogue_swiglu_bwd(const GemmKParams& p, const float (&acc)[32], const uint4 (&rg)[4], const uint4 (&ru)[4],
+                                                         int row_base, int f0, uint8_t* stg, int lane) {
+  uint32_t pdg[16], pdu[16];
+  const uint32_t* g32 = reinterpret_cast<const uint32_t*>(rg);
+  const uint32_t* u32 = reinterpret_cast<const uint32_t*>(ru);
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float2 d = unpack_bf16x2(pack_bf16x2(acc[2 * t] * p.alpha, acc[2 * t + 1] * p.alpha));   // dh rounded to bf16 like the stored tensor
+    const float2 g = unpack_bf16x2(g32[t]), u = unpack_bf16x2(u32[t]);
+    float dg0, du0, dg1, du1;
+    swiglu_bwd_elem(g.x, u.x, d.x, dg0, du0);
+    swiglu_bwd_elem(g.y, u.y, d.y, dg1, du1);
+    pdg[t] = pack_bf16x2(dg0, dg1);
+    pdu[t] = pack_bf16x2(du0, du1);
+  }
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  const int col_g = (f0 >> 6) * 128 + (f0 & 63);
+  gemm_store_chunk_bf16(out, p.ldo, p.M, 2 * p.N, pdg, row_base, col_g, stg, lane);
+  gemm_store_chunk_bf16(out, p.ldo, p.M, 2 * p.N, pdu, row_base, col_g + 64, stg, lane);
 }
 
 }  // namespace slam

@@ -17,6 +17,7 @@ data-parallel exchange is one NCCL all-reduce and the optimizer is one kernel.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -308,6 +309,12 @@ class LlamaLoRAB200:
             return (1.0 + torch.randn(cfg.d, generator=gen, device=dev) * std).to(BF16)
 
         self.embed = base("model.embed_tokens.weight", (cfg.vocab, cfg.d))
+        # Fused SwiGLU (GEMM epilogues act 3 / 4): without LoRA on gate/up the concatenated gate/up weight is stored "blocked-64"
+        # (64 gate rows, then the 64 up rows of the same features, ...) so that a GEMM tile holds both halves of a feature pair.
+        # With adapters on gate/up the HF [gate | up] order is kept (their gradient slices address whole projections).
+        lora_targets = set(lora.targets) if lora is not None else set()
+        self.fuse_swiglu = not ({"gate_proj", "up_proj"} & lora_targets) and cfg.ffn % 64 == 0 and os.environ.get("SLAM_FUSE_SWIGLU", "1") != "0"
+        self.fuse_swiglu_bwd = self.fuse_swiglu and os.environ.get("SLAM_FUSE_SWIGLU_BWD", "1") != "0"
         self.layers = []
         for i in range(L):
             p = f"model.layers.{i}."
@@ -316,7 +323,10 @@ class LlamaLoRAB200:
             del q, k, v
             wo = base(p + "self_attn.o_proj.weight", linear_shape(cfg, "o_proj"))
             g_, u_ = (base(p + f"mlp.{n}.weight", linear_shape(cfg, n)) for n in ("gate_proj", "up_proj"))
-            wgu = torch.cat([g_, u_], 0).contiguous()
+            if self.fuse_swiglu:
+                wgu = torch.stack([g_.view(cfg.ffn // 64, 64, cfg.d), u_.view(cfg.ffn // 64, 64, cfg.d)], 1).reshape(2 * cfg.ffn, cfg.d).contiguous()
+            else:
+                wgu = torch.cat([g_, u_], 0).contiguous()
             del g_, u_
             wd = base(p + "mlp.down_proj.weight", linear_shape(cfg, "down_proj"))
             self.layers.append(dict(wqkv=wqkv, wqkvT=ops.transpose(wqkv), wo=wo, woT=ops.transpose(wo), wgu=wgu, wguT=ops.transpose(wgu),
@@ -490,8 +500,12 @@ class LlamaLoRAB200:
             attn2 = attn.view(M, Dq)
             x2, sv_o = self._lin_fwd(attn2, Lw["wo"], "o", li, residual=x)
             xn2, rstd2 = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=save)
-            gu, sv_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
-            hmid = ops.swiglu_fwd(gu)
+            if self.fuse_swiglu:
+                hmid = torch.empty((M, cfg.ffn), device=x.device, dtype=BF16)
+                gu, sv_gu = ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid), None        # gu (blocked-64) and silu(g) * u from one epilogue
+            else:
+                gu, sv_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
+                hmid = ops.swiglu_fwd(gu)
             x3, sv_d = self._lin_fwd(hmid, Lw["wd"], "down", li, residual=x2)
             if save:
                 saved_layers.append(dict(x=x, rstd1=rstd1, qkv=qkv, attn=attn, lse=lse, x2=x2, rstd2=rstd2, gu=gu,
@@ -516,8 +530,11 @@ class LlamaLoRAB200:
         for li in range(cfg.layers - 1, -1, -1):
             Lw, kp = self.layers[li], sv["layers"][li]
             # ---- MLP block: x3 = x2 + down(silu(g) * u)
-            dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
-            dgu = ops.swiglu_bwd(kp["gu"], dhmid)
+            if self.fuse_swiglu_bwd and "down" not in self.groups:
+                dgu = ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"])                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
+            else:
+                dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
+                dgu = ops.swiglu_bwd(kp["gu"], dhmid, block=64 if self.fuse_swiglu else 0)
             dxn2 = self._lin_bwd(dgu, Lw["wguT"], "gu", li, kp["sv_gu"])
             dx2 = ops.rmsnorm_bwd(dxn2, kp["x2"], Lw["ln2"], kp["rstd2"], dres=dx)
             # ---- attention block: x2 = x + o(attn(rope(qkv(norm(x)))))

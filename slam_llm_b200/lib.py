@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("split_k", _i32),
         ("workspace", _vp), ("workspace_bytes", _i64),
         ("tail_split", _i32), ("reserved", _i32),
+        ("aux", _vp), ("ld_aux", _i64),
     ]
 
 
@@ -77,8 +78,8 @@ _SIGS = {
     "slam_rmsnorm_fwd": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
     "slam_rmsnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
     "slam_rope": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
-    "slam_swiglu_fwd": [_vp, _vp, _i32, _i32, _vp],
-    "slam_swiglu_bwd": [_vp, _vp, _vp, _i32, _i32, _vp],
+    "slam_swiglu_fwd": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "slam_swiglu_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "slam_dropout": [_vp, _vp, _i64, _f32, C.c_uint64, _vp],
     "slam_dropout_bwd_add": [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp],
     "slam_cross_entropy": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
@@ -121,8 +122,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.slam_abi_version() != 2:
-        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 2")
+    if lib.slam_abi_version() != 3:
+        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 3")
     _lib = lib
     return lib
 

@@ -71,9 +71,12 @@ def _gemm_workspace(device: torch.device) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1, tail_split: int = 0) -> torch.Tensor:
+         act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1, tail_split: int = 0,
+         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16.
-    tail_split: 0 = automatic, -1 = off, n > 1 = at most n k-slices per tail tile."""
+    tail_split: 0 = automatic, -1 = off, n > 1 = at most n k-slices per tail tile.
+    act 3 / 4 = fused SwiGLU forward / backward on the blocked-64 gate/up layout (see slam_gemm_args.aux): act 3 returns gu and
+    writes h = silu(g) * u to aux [M, N/2]; act 4 reads gu from aux [M, 2N] and returns d(gu) [M, 2N] (the product dh is not stored)."""
     _req(a, BF16, "gemm.a"); _req(b, BF16, "gemm.b")
     M, K1 = a.shape
     N = b.shape[0]
@@ -82,8 +85,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
         assert out_f32 and bias is None and residual is None and act == 0, "split_k needs a plain f32 output"
         if out is None:
             out = torch.zeros((M, N), device=a.device, dtype=F32)          # k-slices are merged with atomics
+    out_cols = 2 * N if act == 4 else N
     if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=F32 if out_f32 else BF16)
+        out = torch.empty((M, out_cols), device=a.device, dtype=F32 if out_f32 else BF16)
     g = _l.GemmArgs()
     g.a, g.lda = a.data_ptr(), _row_major_2d(a, "gemm.a")
     g.b, g.ldb = b.data_ptr(), _row_major_2d(b, "gemm.b")
@@ -97,7 +101,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     else:
         g.k2 = 0
     _req(out, F32 if out_f32 else BF16, "gemm.out")
-    assert tuple(out.shape) == (M, N)
+    assert tuple(out.shape) == (M, out_cols)
     g.out, g.ldo = out.data_ptr(), _row_major_2d(out, "gemm.out")
     g.out_f32 = 1 if out_f32 else 0
     g.act = act
@@ -113,6 +117,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
         g.residual, g.ldr = None, 0
     g.alpha = alpha
     g.m, g.n = M, N
+    if act >= 3:
+        _req(aux, BF16, "gemm.aux")
+        assert tuple(aux.shape) == ((M, N // 2) if act == 3 else (M, 2 * N)), (aux.shape, M, N, act)
+        g.aux, g.ld_aux = aux.data_ptr(), _row_major_2d(aux, "gemm.aux")
+    else:
+        g.aux, g.ld_aux = None, 0
     g.block_n = block_n
     g.split_k = split_k
     if tail_split == 0:
@@ -311,23 +321,23 @@ def rope_(x: torch.Tensor, n_heads: int, dh: int, seq_len: int, cos: torch.Tenso
     return x
 
 
-def swiglu_fwd(gu, out=None):
+def swiglu_fwd(gu, out=None, block: int = 0):
     _req(gu, BF16, "swiglu.gu")
     assert gu.dim() == 2 and gu.is_contiguous()
     rows, f2 = gu.shape
     if out is None:
         out = torch.empty((rows, f2 // 2), device=gu.device, dtype=BF16)
-    _l.check(_l.load().slam_swiglu_fwd(gu.data_ptr(), out.data_ptr(), rows, f2 // 2, _stream()), "slam_swiglu_fwd")
+    _l.check(_l.load().slam_swiglu_fwd(gu.data_ptr(), out.data_ptr(), rows, f2 // 2, block, _stream()), "slam_swiglu_fwd")
     return out
 
 
-def swiglu_bwd(gu, dh, out=None):
+def swiglu_bwd(gu, dh, out=None, block: int = 0):
     _req(gu, BF16, "swiglu_bwd.gu"); _req(dh, BF16, "swiglu_bwd.dh")
     assert gu.is_contiguous() and dh.is_contiguous()
     rows, f2 = gu.shape
     if out is None:
         out = torch.empty_like(gu)
-    _l.check(_l.load().slam_swiglu_bwd(gu.data_ptr(), dh.data_ptr(), out.data_ptr(), rows, f2 // 2, _stream()), "slam_swiglu_bwd")
+    _l.check(_l.load().slam_swiglu_bwd(gu.data_ptr(), dh.data_ptr(), out.data_ptr(), rows, f2 // 2, block, _stream()), "slam_swiglu_bwd")
     return out
 
 

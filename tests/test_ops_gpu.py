@@ -96,6 +96,39 @@ def test_gemm_dual_segment_lora(ops, tile):
     assert rel_err(only_base, ref) > 2e-2  # the second segment really contributes
 
 
+def _block64(w_gate, w_up):
+    f, d = w_gate.shape
+    return torch.stack([w_gate.view(f // 64, 64, d), w_up.view(f // 64, 64, d)], 1).reshape(2 * f, d).contiguous()
+
+
+@pytest.mark.parametrize("M,F,K,tile", [(300, 512, 256, 0), (1604, 1792, 512, 128256), (1604, 1792, 512, 2000256), (77, 128, 64, 128128), (520, 1024, 320, 256256)])
+def test_gemm_fused_swiglu(ops, M, F, K, tile):
+    """act 3 / 4 (HF LlamaMLP gate/up -> silu * up, and its backward) against the unfused kernels on the blocked-64 layout:
+    the epilogues compute from the bf16-rounded tensors, so the results are bit-identical."""
+    x, wg, wu = rnd(M, K, seed=94), rnd(F, K, scale=0.1, seed=95), rnd(F, K, scale=0.1, seed=96)
+    wgu = _block64(wg, wu)
+    gu_ref = ops.gemm(x, wgu, block_n=tile, tail_split=-1)     # (the fused epilogues never split the tail: same summation order)
+    h_ref = ops.swiglu_fwd(gu_ref, block=64)
+    h = torch.empty(M, F, device=dev(), dtype=BF16)
+    gu = ops.gemm(x, wgu, act=3, aux=h, block_n=tile)
+    assert torch.equal(gu, gu_ref) and torch.equal(h, h_ref)
+    # the blocked layout is a permutation of the HF [gate | up] layout
+    g_hf = ops.gemm(x, torch.cat([wg, wu], 0).contiguous(), tail_split=-1)
+    assert torch.equal(ops.swiglu_fwd(g_hf), h_ref)
+    # backward: dh = dy @ W_down^T-like product [M, F], then d(gu)
+    dy, wd = rnd(M, K, seed=97), rnd(F, K, scale=0.1, seed=98)
+    dh = ops.gemm(dy, wd, block_n=tile if tile % 1000 != 0 else 0, tail_split=-1)
+    dgu_ref = ops.swiglu_bwd(gu_ref, dh, block=64)
+    dgu = ops.gemm(dy, wd, act=4, aux=gu_ref, block_n=tile if tile % 1000 != 0 else 0)
+    assert torch.equal(dgu, dgu_ref)
+    # and against torch autograd of silu(g) * u in fp32 (tolerance: bf16 inputs/outputs)
+    gr = gu_ref.view(M, F // 64, 2, 64)[:, :, 0].reshape(M, F).float().requires_grad_(True)
+    ur = gu_ref.view(M, F // 64, 2, 64)[:, :, 1].reshape(M, F).float().requires_grad_(True)
+    (torch.nn.functional.silu(gr) * ur).backward(dh.float())
+    got = dgu.view(M, F // 64, 2, 64)
+    assert rel_err(got[:, :, 0].reshape(M, F), gr.grad) < 8e-3 and rel_err(got[:, :, 1].reshape(M, F), ur.grad) < 8e-3
+
+
 @pytest.mark.parametrize("M,N,K,tile", [(1604, 4096, 4096, 128256), (1604, 6144, 4096, 128256), (308, 4096, 32064, 128256), (1604, 4096, 4096, 128192),
                                         (300, 776, 1280, 128128), (77, 264, 256, 128256)])
 def test_gemm_tail_split(ops, M, N, K, tile):
