@@ -87,6 +87,7 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long 
 template <int DH, int MT>
 __global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_kernel(const AttnP p) {
   pdl_trigger();
+  pdl_wait();
   constexpr int BM = 64 * MT, BN = 64, PITCH = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_k
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 __global__ void attn_delta_kernel(const AttnP p, int dh) {
   pdl_trigger();
+  pdl_wait();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int total = p.batch * p.sq * p.hq;
@@ -300,6 +302,7 @@ __global__ void attn_delta_kernel(const AttnP p, int dh) {
 template <int DH, int BQ>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
   pdl_trigger();
+  pdl_wait();
   constexpr int BN = 64, PITCH = DH + 8, SPITCH = BQ + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sK = reinterpret_cast<bf16*>(smem_attn);
@@ -508,6 +511,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
 __global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __restrict__ dk, long long lddk, bf16* __restrict__ dv, long long lddv,
                                       long long rows, int hq, int hkv, int dh) {
   pdl_trigger();
+  pdl_wait();
   const int g = hq / hkv;
   const int vec_per_row = hkv * dh / 8;
   const long long total = 2 * rows * vec_per_row;
@@ -536,6 +540,7 @@ __global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __res
 // dq_accum f32 [B,Sq,Hq,DH] -> dq bf16 with row stride lddq
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq, long long rows, int width) {
   pdl_trigger();
+  pdl_wait();
   const int vpr = width / 4;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = rows * vpr;
@@ -589,7 +594,7 @@ static int launch_fwd(const AttnP& p, cudaStream_t st) {
     set = true;
   }
   dim3 grid(static_cast<unsigned>(ceil_div(p.sq, 64 * MT)), p.hq, p.batch);
-  attn_fwd_kernel<DH, MT><<<grid, 128, SMEM, st>>>(p);
+  launch_pdl(attn_fwd_kernel<DH, MT>, grid, 128, SMEM, st, p);
   SLAM_LAUNCH_CHECK("slam_attn_fwd");
   return 0;
 }
@@ -602,7 +607,7 @@ static int launch_bwd(const AttnP& p, cudaStream_t st) {
     set = true;
   }
   dim3 grid(static_cast<unsigned>(ceil_div(p.sk, 64)), p.dkv_part != nullptr ? p.hq : p.hkv, p.batch);
-  attn_bwd_kernel<DH, BQ><<<grid, 128, SMEM, st>>>(p);
+  launch_pdl(attn_bwd_kernel<DH, BQ>, grid, 128, SMEM, st, p);
   SLAM_LAUNCH_CHECK("slam_attn_bwd");
   return 0;
 }
@@ -650,7 +655,7 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
     return static_cast<int>(e);
   }
   const int total_warps = p.batch * p.sq * p.hq;
-  attn_delta_kernel<<<static_cast<unsigned>(ceil_div(total_warps, 8)), 256, 0, st>>>(p, a->dh);
+  launch_pdl(attn_delta_kernel, static_cast<unsigned>(ceil_div(total_warps, 8)), 256, 0, st, p, a->dh);
   SLAM_LAUNCH_CHECK("slam_attn_bwd.delta");
   rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
   if (rc != 0) return rc;
@@ -658,14 +663,14 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
     const long long krows = static_cast<long long>(p.batch) * p.sk;
     long long gb = ceil_div(2 * krows * (p.hkv * a->dh / 8), 256);
     if (gb > num_sms() * 16) gb = num_sms() * 16;
-    attn_group_sum_kernel<<<static_cast<unsigned>(gb), 256, 0, st>>>(p.dkv_part, p.dk, p.lddk, p.dv, p.lddv, krows, p.hq, p.hkv, a->dh);
+    launch_pdl(attn_group_sum_kernel, static_cast<unsigned>(gb), 256, 0, st, p.dkv_part, p.dk, p.lddk, p.dv, p.lddv, krows, p.hq, p.hkv, a->dh);
     SLAM_LAUNCH_CHECK("slam_attn_bwd.group_sum");
   }
   SLAM_CHECK_ARG(p.lddq >= width || p.hq * a->dh <= p.lddq, "attn_bwd: lddq too small");
   const long long nvec = rows * (width / 4);
   long long blocks = ceil_div(nvec, 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  attn_dq_convert_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p.dq_accum, p.dq, p.lddq, rows, width);
+  launch_pdl(attn_dq_convert_kernel, static_cast<unsigned>(blocks), 256, 0, st, p.dq_accum, p.dq, p.lddq, rows, width);
   SLAM_LAUNCH_CHECK("slam_attn_bwd.convert");
   return 0;
 }

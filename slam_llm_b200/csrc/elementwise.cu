@@ -39,6 +39,7 @@ __device__ __forceinline__ float block_sum(float v, float* sbuf) {
 // ---------------------------------------------------------------- casts / adds
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n, float scale) {
   pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -53,6 +54,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -67,6 +70,8 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restri
   }
 }
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -84,6 +89,7 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 }
 __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ yv, bf16* __restrict__ dx, int64_t n) {
   pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -111,6 +117,7 @@ static inline int ew_grid(int64_t n, int per_thread, int threads) {
 // ---------------------------------------------------------------- transpose (bf16, 64x64 tiles via smem)
 __global__ void transpose_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy, int rows, int cols) {
   pdl_trigger();
+  pdl_wait();
   __shared__ bf16 tile[64][66];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
@@ -127,6 +134,8 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, b
 
 // batched f32 transpose: dst[b][j][i] = src[b][i][j]   (conv1d weight-gradient layout change, small)
 __global__ void transpose_f32_batched_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const float* s = src + static_cast<int64_t>(b) * rows * cols;
@@ -147,6 +156,7 @@ __global__ void transpose_f32_batched_kernel(const float* __restrict__ src, floa
 // ---------------------------------------------------------------- row gather / scatter (d % 8 == 0)
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ idx, bf16* __restrict__ y, int n_idx, int d, int scatter) {
   pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x;
   if (i >= n_idx) return;
   const int64_t src = scatter ? i : idx[i];
@@ -158,6 +168,8 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __
 
 // ---------------------------------------------------------------- column sums (bias grads)
 __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   // block = 32 columns x 8 row-lanes; grid.y splits rows; atomics merge partial sums
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -178,6 +190,8 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, int rows,
   }
 }
 __global__ void zero_f32_kernel(float* p, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) p[i] = 0.0f;
@@ -188,6 +202,7 @@ template <int VPT>  // 8-element vectors per thread held in registers
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                           float* __restrict__ rstd_out, int d, float eps) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * d);
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                           bf16* __restrict__ dx, int d) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const int nvec = d / 8;
@@ -277,6 +293,7 @@ template <int VPT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                         bf16* __restrict__ y, int d, float eps) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float sbuf[32];
   const int64_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * d);
@@ -330,6 +347,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                                float* __restrict__ rstd_out, int rows, int d, float eps) {
   pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -361,6 +379,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_warp_kernel(const bf16* __res
                                                                const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                                bf16* __restrict__ dx, int rows, int d) {
   pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -402,6 +421,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_warp_kernel(const bf16* __res
 __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                              bf16* __restrict__ y, int rows, int d, float eps) {
   pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -464,6 +484,8 @@ __device__ __forceinline__ float row_sum(float v, float* s_red) {
 template <int NV, int TPR>
 __global__ void __launch_bounds__(256) rmsnorm_fwd_reg_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                               float* __restrict__ rstd_out, int rows, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
   __shared__ float s_red[8];
   pdl_trigger();
@@ -503,6 +525,8 @@ template <int NV, int TPR>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_reg_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                               const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                               bf16* __restrict__ dx, int rows) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
   __shared__ float s_red[8];
   pdl_trigger();
@@ -558,6 +582,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_reg_kernel(const bf16* __rest
 template <int NV, int TPR>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                             bf16* __restrict__ y, int rows, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = NV * TPR * 8, RPC = 256 / TPR;
   __shared__ float s_red[8];
   pdl_trigger();
@@ -616,6 +642,7 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const bf16* __restri
 __global__ void rope_kernel(bf16* __restrict__ x, int64_t ld, int rows, int seq_len, int n_heads, int dh, const float* __restrict__ cosT,
                             const float* __restrict__ sinT, int inverse) {
   pdl_trigger();
+  pdl_wait();
   const int half = dh / 2;
   const int vec_per_head = half / 8;
   const int64_t total = static_cast<int64_t>(rows) * n_heads * vec_per_head;
@@ -658,6 +685,7 @@ __device__ __forceinline__ void swiglu_cols(int c, int f, int block, int& gcol, 
 }
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, int rows, int f, int block) {
   pdl_trigger();
+  pdl_wait();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -677,6 +705,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
 }
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dh, bf16* __restrict__ dgu, int rows, int f, int block) {
   pdl_trigger();
+  pdl_wait();
   const int vpr = f / 8;
   const int64_t total = static_cast<int64_t>(rows) * vpr;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -733,6 +762,7 @@ __device__ __forceinline__ void mask_span(const uint8_t* __restrict__ mrow, int 
 __global__ void embed_merge_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, const bf16* __restrict__ audio, int ta,
                                    const bf16* __restrict__ embed, bf16* __restrict__ x, int s, int d) {
   pdl_trigger();
+  pdl_wait();
   __shared__ int sh[2];
   const int b = blockIdx.y, r = blockIdx.x;
   const uint8_t* mrow = mask + static_cast<int64_t>(b) * s;
@@ -758,6 +788,8 @@ __global__ void embed_merge_kernel(const int64_t* __restrict__ ids, const uint8_
   }
 }
 __global__ void embed_merge_bwd_kernel(const uint8_t* __restrict__ mask, const bf16* __restrict__ dx, bf16* __restrict__ daudio, int ta, int s, int d) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int sh[2];
   const int b = blockIdx.y, j = blockIdx.x;  // j: audio row
   int start, len;
@@ -774,6 +806,7 @@ __global__ void embed_merge_bwd_kernel(const uint8_t* __restrict__ mask, const b
 template <typename TIn>
 __global__ void im2col_kernel(const TIn* __restrict__ x, int t_in, int c, int stride, int t_out, bf16* __restrict__ col, int64_t ldk) {
   pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, t = blockIdx.x;
   bf16* out = col + (static_cast<int64_t>(b) * t_out + t) * ldk;
   for (int j = threadIdx.x; j < ldk; j += blockDim.x) {
@@ -791,6 +824,7 @@ __global__ void im2col_kernel(const TIn* __restrict__ x, int t_in, int c, int st
 }
 __global__ void add_pos_kernel(bf16* __restrict__ x, const float* __restrict__ pos, int t, int d, int64_t total_vec) {
   pdl_trigger();
+  pdl_wait();
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int vpr = d / 8;
@@ -819,6 +853,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
 // y = x * keep / (1 - p)
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n, uint32_t thresh, float inv_keep, uint64_t seed) {
   pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -833,6 +868,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 __global__ void dropout_bwd_add_kernel(const bf16* __restrict__ base, const bf16* __restrict__ lora, bf16* __restrict__ out, int64_t n, uint32_t thresh,
                                        float inv_keep, uint64_t seed) {
   pdl_trigger();
+  pdl_wait();
   int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -848,6 +884,8 @@ __global__ void dropout_bwd_add_kernel(const bf16* __restrict__ base, const bf16
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics, single tensor, fp32)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                              float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_div) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) {
@@ -876,64 +914,64 @@ extern "C" {
 int slam_cast_f32_to_bf16(const float* x, void* y, int64_t n, float scale, void* stream) {
   SLAM_CHECK_ARG(n >= 0, "cast: n < 0");
   if (n == 0) return 0;
-  cast_f32_bf16_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(x, BF(y), n, scale);
+  launch_pdl(cast_f32_bf16_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), x, BF(y), n, scale);
   SLAM_LAUNCH_CHECK("slam_cast_f32_to_bf16");
   return 0;
 }
 int slam_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
   if (n == 0) return 0;
-  cast_bf16_f32_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(x), y, n);
+  launch_pdl(cast_bf16_f32_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), CBF(x), y, n);
   SLAM_LAUNCH_CHECK("slam_cast_bf16_to_f32");
   return 0;
 }
 int slam_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) {
   if (n == 0) return 0;
-  add_bf16_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), BF(y), n);
+  launch_pdl(add_bf16_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), CBF(a), CBF(b), BF(y), n);
   SLAM_LAUNCH_CHECK("slam_add_bf16");
   return 0;
 }
 int slam_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
   if (n == 0) return 0;
-  relu_bwd_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(dx), n);
+  launch_pdl(relu_bwd_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), CBF(dy), CBF(y), BF(dx), n);
   SLAM_LAUNCH_CHECK("slam_relu_bwd");
   return 0;
 }
 int slam_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream) {
   SLAM_CHECK_ARG(rows > 0 && cols > 0, "transpose: bad shape");
   dim3 grid(static_cast<unsigned>(ceil_div(cols, 64)), static_cast<unsigned>(ceil_div(rows, 64)));
-  transpose_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, rows, cols);
+  launch_pdl(transpose_bf16_kernel, grid, 256, 0, ST(stream), CBF(x), ldx, BF(y), ldy, rows, cols);
   SLAM_LAUNCH_CHECK("slam_transpose_bf16");
   return 0;
 }
 int slam_transpose_f32_batched(const float* src, float* dst, int32_t batch, int32_t rows, int32_t cols, void* stream) {
   SLAM_CHECK_ARG(batch > 0 && rows > 0 && cols > 0 && batch <= 65535, "transpose_f32_batched: bad shape");
   dim3 grid(static_cast<unsigned>(ceil_div(cols, 32)), static_cast<unsigned>(ceil_div(rows, 32)), batch);
-  transpose_f32_batched_kernel<<<grid, 256, 0, ST(stream)>>>(src, dst, rows, cols);
+  launch_pdl(transpose_f32_batched_kernel, grid, 256, 0, ST(stream), src, dst, rows, cols);
   SLAM_LAUNCH_CHECK("slam_transpose_f32_batched");
   return 0;
 }
 int slam_gather_rows(const void* x, const int32_t* idx, void* y, int32_t n_idx, int32_t d, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0, "gather_rows: d %% 8 != 0");
   if (n_idx == 0) return 0;
-  gather_rows_kernel<<<n_idx, 128, 0, ST(stream)>>>(CBF(x), idx, BF(y), n_idx, d, 0);
+  launch_pdl(gather_rows_kernel, n_idx, 128, 0, ST(stream), CBF(x), idx, BF(y), n_idx, d, 0);
   SLAM_LAUNCH_CHECK("slam_gather_rows");
   return 0;
 }
 int slam_scatter_rows(const void* x, const int32_t* idx, void* y, int32_t n_idx, int32_t d, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0, "scatter_rows: d %% 8 != 0");
   if (n_idx == 0) return 0;
-  gather_rows_kernel<<<n_idx, 128, 0, ST(stream)>>>(CBF(x), idx, BF(y), n_idx, d, 1);
+  launch_pdl(gather_rows_kernel, n_idx, 128, 0, ST(stream), CBF(x), idx, BF(y), n_idx, d, 1);
   SLAM_LAUNCH_CHECK("slam_scatter_rows");
   return 0;
 }
 int slam_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* out, void* stream) {
   SLAM_CHECK_ARG(rows > 0 && cols > 0, "colsum: bad shape");
-  zero_f32_kernel<<<ew_grid(cols, 1, 256), 256, 0, ST(stream)>>>(out, cols);
+  launch_pdl(zero_f32_kernel, ew_grid(cols, 1, 256), 256, 0, ST(stream), out, cols);
   SLAM_LAUNCH_CHECK("slam_colsum.zero");
   int ysplit = static_cast<int>(ceil_div(rows, 256));
   if (ysplit > 64) ysplit = 64;
   dim3 grid(static_cast<unsigned>(ceil_div(cols, 32)), static_cast<unsigned>(ysplit));
-  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), ldx, rows, cols, out);
+  launch_pdl(colsum_kernel, grid, 256, 0, ST(stream), CBF(x), ldx, rows, cols, out);
   SLAM_LAUNCH_CHECK("slam_colsum");
   return 0;
 }
@@ -952,11 +990,11 @@ int slam_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int32_t
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "rmsnorm_fwd: bad shape rows=%d d=%d", rows, d);
   bool done = false;
 #define SLAM_L(NV, TPR)                                                                                                                  \
-  rmsnorm_fwd_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(x), CBF(w), BF(y), rstd, rows, eps); \
+  launch_pdl(rmsnorm_fwd_reg_kernel<NV, TPR>, static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream), CBF(x), CBF(w), BF(y), rstd, rows, eps); \
   done = true
   SLAM_NORM_DISPATCH(d, SLAM_L)
 #undef SLAM_L
-  if (!done) rmsnorm_fwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), CBF(w), BF(y), rstd, rows, d, eps);
+  if (!done) launch_pdl(rmsnorm_fwd_warp_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream), CBF(x), CBF(w), BF(y), rstd, rows, d, eps);
   SLAM_LAUNCH_CHECK("slam_rmsnorm_fwd");
   return 0;
 }
@@ -965,13 +1003,13 @@ int slam_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "rmsnorm_bwd: bad shape rows=%d d=%d", rows, d);
   bool done = false;
 #define SLAM_L(NV, TPR)                                                                                                                 \
-  rmsnorm_bwd_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), \
+  launch_pdl(rmsnorm_bwd_reg_kernel<NV, TPR>, static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream), CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), \
                                                                                                          BF(dx), rows);                \
   done = true
   SLAM_NORM_DISPATCH(d, SLAM_L)
 #undef SLAM_L
   if (!done)
-    rmsnorm_bwd_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), rows, d);
+    launch_pdl(rmsnorm_bwd_warp_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream), CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), rows, d);
   SLAM_LAUNCH_CHECK("slam_rmsnorm_bwd");
   return 0;
 }
@@ -979,11 +1017,11 @@ int slam_layernorm(const void* x, const float* w, const float* b, void* y, int32
   SLAM_CHECK_ARG(d % 8 == 0 && rows > 0, "layernorm: bad shape rows=%d d=%d", rows, d);
   bool done = false;
 #define SLAM_L(NV, TPR)                                                                                                       \
-  layernorm_reg_kernel<NV, TPR><<<static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream)>>>(CBF(x), w, b, BF(y), rows, eps); \
+  launch_pdl(layernorm_reg_kernel<NV, TPR>, static_cast<unsigned>(ceil_div(rows, 256 / TPR)), 256, 0, ST(stream), CBF(x), w, b, BF(y), rows, eps); \
   done = true
   SLAM_NORM_DISPATCH(d, SLAM_L)
 #undef SLAM_L
-  if (!done) layernorm_warp_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream)>>>(CBF(x), w, b, BF(y), rows, d, eps);
+  if (!done) launch_pdl(layernorm_warp_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, ST(stream), CBF(x), w, b, BF(y), rows, d, eps);
   SLAM_LAUNCH_CHECK("slam_layernorm");
   return 0;
 }
@@ -991,19 +1029,19 @@ int slam_rope(void* x, int64_t ld, int32_t rows, int32_t seq_len, int32_t n_head
               int32_t inverse, void* stream) {
   SLAM_CHECK_ARG(dh % 16 == 0 && ld % 8 == 0, "rope: dh %% 16 != 0 or ld %% 8 != 0");
   const int64_t total = static_cast<int64_t>(rows) * n_heads * (dh / 16);
-  rope_kernel<<<ew_grid(total, 1, 256), 256, 0, ST(stream)>>>(BF(x), ld, rows, seq_len, n_heads, dh, cos_t, sin_t, inverse);
+  launch_pdl(rope_kernel, ew_grid(total, 1, 256), 256, 0, ST(stream), BF(x), ld, rows, seq_len, n_heads, dh, cos_t, sin_t, inverse);
   SLAM_LAUNCH_CHECK("slam_rope");
   return 0;
 }
 int slam_swiglu_fwd(const void* gu, void* h, int32_t rows, int32_t f, int32_t block, void* stream) {
   SLAM_CHECK_ARG(f % 8 == 0 && (block == 0 || (block % 8 == 0 && f % block == 0)), "swiglu: f %% 8 != 0 or bad block");
-  swiglu_fwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), BF(h), rows, f, block);
+  launch_pdl(swiglu_fwd_kernel, ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream), CBF(gu), BF(h), rows, f, block);
   SLAM_LAUNCH_CHECK("slam_swiglu_fwd");
   return 0;
 }
 int slam_swiglu_bwd(const void* gu, const void* dh, void* dgu, int32_t rows, int32_t f, int32_t block, void* stream) {
   SLAM_CHECK_ARG(f % 8 == 0 && (block == 0 || (block % 8 == 0 && f % block == 0)), "swiglu: f %% 8 != 0 or bad block");
-  swiglu_bwd_kernel<<<ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream)>>>(CBF(gu), CBF(dh), BF(dgu), rows, f, block);
+  launch_pdl(swiglu_bwd_kernel, ew_grid(static_cast<int64_t>(rows) * f / 8, 1, 256), 256, 0, ST(stream), CBF(gu), CBF(dh), BF(dgu), rows, f, block);
   SLAM_LAUNCH_CHECK("slam_swiglu_bwd");
   return 0;
 }
@@ -1011,14 +1049,14 @@ int slam_embed_merge(const int64_t* ids, const uint8_t* mask, const void* audio,
                      int32_t s, int32_t d, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0 && batch > 0 && s > 0, "embed_merge: bad shape");
   dim3 grid(s, batch);
-  embed_merge_kernel<<<grid, 128, 0, ST(stream)>>>(ids, mask, CBF(audio), ta, CBF(embed), BF(x), s, d);
+  launch_pdl(embed_merge_kernel, grid, 128, 0, ST(stream), ids, mask, CBF(audio), ta, CBF(embed), BF(x), s, d);
   SLAM_LAUNCH_CHECK("slam_embed_merge");
   return 0;
 }
 int slam_embed_merge_bwd(const uint8_t* mask, const void* dx, void* daudio, int32_t ta, int32_t batch, int32_t s, int32_t d, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0 && batch > 0 && s > 0 && ta > 0, "embed_merge_bwd: bad shape");
   dim3 grid(ta, batch);
-  embed_merge_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(mask, CBF(dx), BF(daudio), ta, s, d);
+  launch_pdl(embed_merge_bwd_kernel, grid, 128, 0, ST(stream), mask, CBF(dx), BF(daudio), ta, s, d);
   SLAM_LAUNCH_CHECK("slam_embed_merge_bwd");
   return 0;
 }
@@ -1029,16 +1067,16 @@ int slam_conv_im2col(const void* x, int32_t x_is_f32, int32_t batch, int32_t t_i
   const int t_out = (t_in + 2 - 3) / stride + 1;
   dim3 grid(t_out, batch);
   if (x_is_f32)
-    im2col_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), t_in, c, stride, t_out, BF(col), ldk);
+    launch_pdl(im2col_kernel<float>, grid, 256, 0, ST(stream), reinterpret_cast<const float*>(x), t_in, c, stride, t_out, BF(col), ldk);
   else
-    im2col_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(CBF(x), t_in, c, stride, t_out, BF(col), ldk);
+    launch_pdl(im2col_kernel<bf16>, grid, 256, 0, ST(stream), CBF(x), t_in, c, stride, t_out, BF(col), ldk);
   SLAM_LAUNCH_CHECK("slam_conv_im2col");
   return 0;
 }
 int slam_add_pos(void* x, const float* pos, int32_t batch, int32_t t, int32_t d, void* stream) {
   SLAM_CHECK_ARG(d % 8 == 0, "add_pos: d %% 8 != 0");
   const int64_t total = static_cast<int64_t>(batch) * t * d / 8;
-  add_pos_kernel<<<ew_grid(total, 1, 256), 256, 0, ST(stream)>>>(BF(x), pos, t, d, total);
+  launch_pdl(add_pos_kernel, ew_grid(total, 1, 256), 256, 0, ST(stream), BF(x), pos, t, d, total);
   SLAM_LAUNCH_CHECK("slam_add_pos");
   return 0;
 }
@@ -1049,14 +1087,14 @@ static inline uint32_t drop_thresh(float p) {
 int slam_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
   SLAM_CHECK_ARG(n % 8 == 0 && p >= 0.0f && p < 1.0f, "dropout: n %% 8 != 0 or p outside [0,1)");
   if (n == 0) return 0;
-  dropout_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
+  launch_pdl(dropout_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), CBF(x), BF(y), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
   SLAM_LAUNCH_CHECK("slam_dropout");
   return 0;
 }
 int slam_dropout_bwd_add(const void* base, const void* lora, void* out, int64_t n, float p, uint64_t seed, void* stream) {
   SLAM_CHECK_ARG(n % 8 == 0 && p >= 0.0f && p < 1.0f, "dropout_bwd_add: n %% 8 != 0 or p outside [0,1)");
   if (n == 0) return 0;
-  dropout_bwd_add_kernel<<<ew_grid(n, 8, 256), 256, 0, ST(stream)>>>(CBF(base), CBF(lora), BF(out), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
+  launch_pdl(dropout_bwd_add_kernel, ew_grid(n, 8, 256), 256, 0, ST(stream), CBF(base), CBF(lora), BF(out), n, drop_thresh(p), 1.0f / (1.0f - p), seed);
   SLAM_LAUNCH_CHECK("slam_dropout_bwd_add");
   return 0;
 }
@@ -1066,7 +1104,7 @@ int slam_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_s
   if (n == 0) return 0;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step_host);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_host);
-  adamw_kernel<<<ew_grid(n, 1, 256), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+  launch_pdl(adamw_kernel, ew_grid(n, 1, 256), 256, 0, ST(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                            static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_div);
   SLAM_LAUNCH_CHECK("slam_adamw");
   return 0;

@@ -138,6 +138,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                        // q / k / v come from the preceding GEMM: wait for it before the first load
   const uint32_t tmem_base = *tmem_slot;             // score tile: columns [0, 128)
   const uint32_t tmem_o = tmem_base + 128;           // output accumulator: columns [128, 128 + DH)
 
@@ -414,7 +415,7 @@ static int fa_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     }
     set = true;
   }
-  fmha_fwd_tc_kernel<DH, MASKED><<<grid, FA_THREADS, FaCfg<DH>::SMEM, st>>>(tq, tk, tv, p);
+  launch_pdl(fmha_fwd_tc_kernel<DH, MASKED>, grid, FA_THREADS, FaCfg<DH>::SMEM, st, tq, tk, tv, p);
   SLAM_LAUNCH_CHECK("slam_attn_fwd.tcgen05");
   return 0;
 }

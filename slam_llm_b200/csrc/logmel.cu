@@ -28,12 +28,16 @@ __device__ __forceinline__ float key_float(int k) {
 }
 
 __global__ void logmel_init_kernel(float* scratch, int batch) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) reinterpret_cast<int*>(scratch)[i] = float_key(-CUDART_INF_F);
 }
 
 __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ wav, int n_samples_max, int n_frames, const int* __restrict__ lengths,
                                                      const float* __restrict__ filt_t, int n_mels, float* __restrict__ out, float* __restrict__ scratch) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_cos[NFFT];
   __shared__ float s_sin[NFFT];
   __shared__ float s_x[FR][NFFT];      // windowed frames
@@ -120,6 +124,8 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
 
 __global__ void logmel_norm_kernel(float* __restrict__ out, const float* __restrict__ scratch, int64_t per_utt, const int* __restrict__ lengths,
                                    int n_samples_max, int n_mels) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const float gmax = key_float(reinterpret_cast<const int*>(scratch)[b]);
   float* o = out + static_cast<int64_t>(b) * per_utt;
@@ -138,14 +144,14 @@ extern "C" int slam_logmel(const float* wav, int32_t batch, int32_t n_samples, c
                  n_samples, n_mels);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_frames = n_samples / HOP;
-  logmel_init_kernel<<<static_cast<unsigned>(ceil_div(batch, 128)), 128, 0, st>>>(scratch_max, batch);
+  launch_pdl(logmel_init_kernel, static_cast<unsigned>(ceil_div(batch, 128)), 128, 0, st, scratch_max, batch);
   SLAM_LAUNCH_CHECK("slam_logmel.init");
   dim3 grid(static_cast<unsigned>(ceil_div(n_frames, FR)), batch);
-  logmel_kernel<<<grid, 256, 0, st>>>(wav, n_samples, n_frames, lengths, filters_t, n_mels, out, scratch_max);
+  launch_pdl(logmel_kernel, grid, 256, 0, st, wav, n_samples, n_frames, lengths, filters_t, n_mels, out, scratch_max);
   SLAM_LAUNCH_CHECK("slam_logmel");
   const int64_t per_utt = static_cast<int64_t>(n_frames) * n_mels;
   dim3 g2(static_cast<unsigned>(ceil_div(per_utt, 256 * 4) > 296 ? 296 : ceil_div(per_utt, 256 * 4)), batch);
-  logmel_norm_kernel<<<g2, 256, 0, st>>>(out, scratch_max, per_utt, lengths, n_samples, n_mels);
+  launch_pdl(logmel_norm_kernel, g2, 256, 0, st, out, scratch_max, per_utt, lengths, n_samples, n_mels);
   SLAM_LAUNCH_CHECK("slam_logmel.norm");
   return 0;
 }

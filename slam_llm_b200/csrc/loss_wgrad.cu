@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(512) cross_entropy_kernel(const float* __restr
                                                             int* __restrict__ n_correct, bf16* __restrict__ dlogits, long long lddl,
                                                             const float* __restrict__ grad_scale) {
   pdl_trigger();
+  pdl_wait();
   __shared__ float s_m[16], s_s[16], s_bv[16];
   __shared__ int s_bi[16];
   __shared__ float s_lse;
@@ -124,6 +125,8 @@ __global__ void __launch_bounds__(512) cross_entropy_kernel(const float* __restr
 template <int PMAX>
 __global__ void __launch_bounds__(256) wgrad_thin_kernel(const bf16* __restrict__ a, long long lda, int pdim, const bf16* __restrict__ bm, long long ldb,
                                                          int qdim, int m, int m_chunk, float scale, float* __restrict__ c, long long ldc) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int MB = 32;
   __shared__ float sA[MB][PMAX];
   __shared__ float sB[MB][64 + 1];
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(128) wgrad_thin_mma_kernel(const bf16* __restr
                                                              long long ldb, int qdim, int m, int m_chunk, float scale, float* __restrict__ c,
                                                              long long ldc) {
   pdl_trigger();
+  pdl_wait();
   constexpr int MC = 64, QT = 256, APITCH = PT * 16 + 8, BPITCH = QT + 8;
   __shared__ __align__(16) bf16 sA[MC * APITCH];
   __shared__ __align__(16) bf16 sB[MC * BPITCH];
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(128) wgrad_thin_mma_kernel(const bf16* __restr
 }
 
 __global__ void zero2d_kernel(float* c, long long ldc, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * cols;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -253,6 +259,7 @@ __global__ void zero2d_kernel(float* c, long long ldc, int rows, int cols) {
 __global__ void pack2d_kernel(const float* __restrict__ src, long long src_bs, long long src_ld, bf16* __restrict__ dst, long long dst_bs,
                               long long dst_ld, int rows, int cols, float scale, int transpose) {
   pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const float* s = src + b * src_bs;
   bf16* d = dst + b * dst_bs;
@@ -281,7 +288,7 @@ int slam_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets,
   SLAM_CHECK_ARG(rows >= 0 && vocab > 0, "cross_entropy: bad shape");
   SLAM_CHECK_ARG(ldl % 4 == 0 && (dlogits == nullptr || lddl % 4 == 0), "cross_entropy: leading dims must be multiples of 4");
   if (rows == 0) return 0;
-  cross_entropy_kernel<<<rows, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ldl, targets, vocab, loss_sum, n_valid, n_correct,
+  launch_pdl(cross_entropy_kernel, rows, 512, 0, reinterpret_cast<cudaStream_t>(stream), logits, ldl, targets, vocab, loss_sum, n_valid, n_correct,
                                                                                 reinterpret_cast<bf16*>(dlogits), lddl, grad_scale);
   SLAM_LAUNCH_CHECK("slam_cross_entropy");
   return 0;
@@ -294,7 +301,7 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long zb = ceil_div(static_cast<long long>(p) * q, 256);
   if (zb > 1184) zb = 1184;
-  zero2d_kernel<<<static_cast<unsigned>(zb), 256, 0, st>>>(c, ldc, p, q);
+  launch_pdl(zero2d_kernel, static_cast<unsigned>(zb), 256, 0, st, c, ldc, p, q);
   SLAM_LAUNCH_CHECK("slam_wgrad_thin.zero");
   const bf16* ap = reinterpret_cast<const bf16*>(a);
   const bf16* bp = reinterpret_cast<const bf16*>(b);
@@ -305,11 +312,11 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
     const int m_chunk = 128;
     dim3 grid(static_cast<unsigned>(ceil_div(q, 256)), static_cast<unsigned>(ceil_div(m, m_chunk)));
     if (p <= 16)
-      wgrad_thin_mma_kernel<1><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+      launch_pdl(wgrad_thin_mma_kernel<1>, grid, 128, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
     else if (p <= 32)
-      wgrad_thin_mma_kernel<2><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+      launch_pdl(wgrad_thin_mma_kernel<2>, grid, 128, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
     else
-      wgrad_thin_mma_kernel<4><<<grid, 128, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+      launch_pdl(wgrad_thin_mma_kernel<4>, grid, 128, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
     SLAM_LAUNCH_CHECK("slam_wgrad_thin.mma");
     return 0;
   }
@@ -324,11 +331,11 @@ int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_
   }
   dim3 grid(qblocks, ysplit);
   if (p <= 16)
-    wgrad_thin_kernel<16><<<grid, 256, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    launch_pdl(wgrad_thin_kernel<16>, grid, 256, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
   else if (p <= 32)
-    wgrad_thin_kernel<32><<<grid, 256, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    launch_pdl(wgrad_thin_kernel<32>, grid, 256, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
   else
-    wgrad_thin_kernel<64><<<grid, 256, 0, st>>>(ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
+    launch_pdl(wgrad_thin_kernel<64>, grid, 256, 0, st, ap, lda, p, bp, ldb, q, m, m_chunk, scale, c, ldc);
   SLAM_LAUNCH_CHECK("slam_wgrad_thin");
   return 0;
 }
@@ -340,7 +347,7 @@ int slam_pack2d(const float* src, int64_t src_batch_stride, int64_t src_ld, void
   long long blocks = ceil_div(static_cast<long long>(rows) * cols, 256);
   if (blocks > 592) blocks = 592;
   dim3 grid(static_cast<unsigned>(blocks), batch);
-  pack2d_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_batch_stride, src_ld, reinterpret_cast<bf16*>(dst_bf16),
+  launch_pdl(pack2d_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), src, src_batch_stride, src_ld, reinterpret_cast<bf16*>(dst_bf16),
                                                                          dst_batch_stride, dst_ld, rows, cols, scale, transpose);
   SLAM_LAUNCH_CHECK("slam_pack2d");
   return 0;
