@@ -288,6 +288,16 @@ class slam_model(nn.Module):
             torch.distributed.all_reduce(self.b200.arena.grad)     # DDP: the one data-path collective (finetune.py:181-184)
         self._bind_grad_views()
 
+    def shadow_backward(self):
+        """DDP `Join` (utils/train_utils.py:91): this rank has no batch for the micro-step while other ranks still train - contribute
+        zero gradients to the step's all-reduce so that every replica applies the same update."""
+        if self.b200.micro_steps == 0:
+            self.b200.arena.grad.zero_()
+        self.b200.micro_steps += 1
+        if self.ddp_world_size > 1 and self.ddp_sync:
+            torch.distributed.all_reduce(self.b200.arena.grad)
+        self._bind_grad_views()
+
     # ---- decoder entry used by recipes that override forward() and call self.llm(...) themselves
     def llm_forward(self, inputs_embeds, attention_mask, labels):
         raise NotImplementedError("calling self.llm(inputs_embeds=...) directly is not wired yet; use slam_model.forward")

@@ -59,6 +59,27 @@ def _move_batch(batch, device):
     return batch
 
 
+def _joined(loader, active: bool, device=None):
+    """DDP `Join` for per-rank iterable loaders of unequal length (the reference wraps its epoch in
+    torch.distributed.algorithms.join.Join, utils/train_utils.py:91, because dynamic-frame batching gives every rank its own
+    number of batches, datasets/speech_dataset_large.py:80-86).  Every rank keeps stepping until ALL ranks are exhausted; a rank
+    that has run dry is handed `None` and must then contribute zero gradients to the collectives of that step
+    (`slam_model.shadow_backward`), exactly what DDP's join hook does (gradients still divided by the initial world size)."""
+    it = iter(loader)
+    if not active:
+        yield from it
+        return
+    flag_dev = device if dist.get_backend() == "nccl" else "cpu"
+    flag = torch.zeros(1, dtype=torch.int32, device=flag_dev)
+    while True:
+        batch = next(it, None)
+        flag.fill_(0 if batch is None else 1)
+        dist.all_reduce(flag)
+        if int(flag.item()) == 0:
+            return
+        yield batch
+
+
 def train(model, train_dataloader, eval_dataloader, tokenizer, optimizer, lr_scheduler, gradient_accumulation_steps, train_config, log_config,
           fsdp_config=None, local_rank=None, rank=None):
     """Returns the results dict of the reference (avg_train_prep / avg_train_loss / ... / avg_checkpoint_time)."""
@@ -84,21 +105,30 @@ def train(model, train_dataloader, eval_dataloader, tokenizer, optimizer, lr_sch
             pbar = tqdm(colour="blue", desc=f"Training Epoch: {epoch+1}", total=total_length, dynamic_ncols=True, disable=not is_main)
             stop = False
             step = -1
-            for step, batch in enumerate(train_dataloader):
-                batch = _move_batch(batch, device)
+            real_steps = 0
+            join = dynamic and distributed and world_size > 1 and dist.is_initialized()
+            for step, batch in enumerate(_joined(train_dataloader, join, device)):
                 last_micro = (step + 1) % gradient_accumulation_steps == 0 or (not dynamic and step == len(train_dataloader) - 1)
                 if hasattr(raw_model, "ddp_sync"):
                     raw_model.ddp_sync = last_micro           # DDP no_sync() on accumulation micro-steps
-                outputs, *rest = model(**batch)
-                acc = rest[0] if rest else -1
-                loss = outputs.loss / gradient_accumulation_steps
-                acc = acc / gradient_accumulation_steps
+                shadow = batch is None                        # Join: this rank is out of data, the others are not
+                real_steps += 0 if shadow else 1
+                if shadow:
+                    raw_model.shadow_backward()
+                    loss, acc = torch.zeros((), device=device), 0.0
+                else:
+                    batch = _move_batch(batch, device)
+                    outputs, *rest = model(**batch)
+                    acc = rest[0] if rest else -1
+                    loss = outputs.loss / gradient_accumulation_steps
+                    acc = acc / gradient_accumulation_steps
                 gstep = (epoch * total_length + step) if not dynamic else step + 1
                 if use_wandb and step % log_config.log_interval == 0 and is_main:
                     wandb.log({"train_inner/train_inner_loss": loss, "train_inner/train_inner_accuracy": acc}, step=gstep)
                 total_loss = total_loss + loss.detach().float()
                 total_acc = total_acc + acc
-                loss.backward()
+                if not shadow:
+                    loss.backward()
                 if last_micro:
                     optimizer.step()
                     if lr_scheduler is not None:
@@ -163,7 +193,7 @@ def train(model, train_dataloader, eval_dataloader, tokenizer, optimizer, lr_sch
         if world_size > 1 and distributed:
             dist.all_reduce(total_loss, op=dist.ReduceOp.SUM)
             dist.all_reduce(total_acc, op=dist.ReduceOp.SUM)
-        n_batches = len(train_dataloader) if not dynamic else (step + 1)
+        n_batches = len(train_dataloader) if not dynamic else max(real_steps, 1)   # (shadow Join steps carry no loss)
         train_epoch_loss = total_loss / n_batches / world_size
         train_epoch_acc = total_acc / n_batches / world_size
         train_perplexity = torch.exp(train_epoch_loss)

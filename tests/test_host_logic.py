@@ -262,6 +262,68 @@ def test_world_size_2_gloo_data_parallel_arithmetic():
     assert out[0][3] == out[1][3] == [0.0] * 3                      # trainables broadcast from rank 0
 
 
+class _JoinMock(_MockModel):
+    """Stand-in with the DDP surface of slam_model: grads all-reduced in backward on sync micro-steps, shadow_backward for Join."""
+    ddp_world_size, ddp_sync = 2, True
+
+    def __init__(self):
+        super().__init__()
+        self.w.register_hook(self._hook)
+        self.shadows = 0
+
+    def _hook(self, g):
+        import torch.distributed as dist
+        if self.ddp_sync:
+            g = g.clone()
+            if self.w.grad is not None:            # accumulated micro-steps ride along with the last one (flat-buffer all-reduce)
+                g += self.w.grad
+                self.w.grad.zero_()
+            dist.all_reduce(g)
+        return g
+
+    def shadow_backward(self):
+        import torch.distributed as dist
+        self.shadows += 1
+        if self.w.grad is None:
+            self.w.grad = torch.zeros_like(self.w)
+        if self.ddp_sync:
+            dist.all_reduce(self.w.grad)
+
+
+def _join_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from slam_llm.utils import train_utils
+    train_utils._device = lambda tc, lr: torch.device("cpu")
+    torch.manual_seed(rank)
+    data = [{"x": torch.randn(2, 4)} for _ in range(5 if rank == 0 else 2)]      # dynamic-frame batching: unequal step counts
+    model = _JoinMock()
+    _CountingSGD.steps = 0
+    opt = _CountingSGD(model.parameters(), lr=0.1)
+    res = train_utils.train(model, iter(data), None, None, opt, None, 1, _train_cfg(enable_ddp=True, batching_strategy="dynamic"),
+                            DictConfig({"use_wandb": False, "log_interval": 5}), rank=rank, local_rank=rank)
+    q.put((rank, model.calls, model.shadows, _CountingSGD.steps, model.w.detach().tolist(), float(res["avg_train_loss"])))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_join_on_uneven_dynamic_batches():
+    """Reference: the epoch runs under torch's Join (utils/train_utils.py:91) because dynamic-frame batching gives ranks different
+    numbers of batches.  Here: the rank that runs dry keeps stepping with zero gradients until every rank is exhausted."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + os.getpid() % 500
+    procs = [ctx.Process(target=_join_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted(q.get(timeout=180) for _ in range(2))
+    [p.join(60) for p in procs]
+    (r0, calls0, sh0, steps0, w0, _), (r1, calls1, sh1, steps1, w1, _) = out
+    assert (calls0, sh0, calls1, sh1) == (5, 0, 2, 3)               # rank 1 shadows the 3 steps it has no data for
+    assert steps0 == steps1 == 5                                    # same number of optimizer steps everywhere
+    assert w0 == w1                                                 # replicas stay identical
+
+
 def test_reference_arm_only_rank0_works(monkeypatch, capsys):
     sys.path.insert(0, ROOT)
     import bench
