@@ -491,8 +491,7 @@ class LlamaLoRAB200:
         for li, Lw in enumerate(self.layers):
             xn1, rstd1 = ops.rmsnorm_fwd(x, Lw["ln1"], cfg.eps, need_rstd=save)
             qkv, sv_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li)
-            ops.rope_(qkv[:, :Dq], H, dh, S, cos, sin)
-            ops.rope_(qkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin)
+            ops.rope_(qkv[:, : Dq + Dkv], H + Hkv, dh, S, cos, sin)                  # q and k heads are adjacent in the fused buffer: one launch
             q = qkv[:, :Dq].view(B, S, H, dh)
             k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
             v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
@@ -546,8 +545,7 @@ class LlamaLoRAB200:
             dqkv = torch.empty_like(qkv)
             ops.attn_bwd(q, k, v, kp["attn"], kp["lse"], dattn.view(B, S, H, dh), causal=True, scale=scale, key_mask=sv["key_mask"],
                          dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh))
-            ops.rope_(dqkv[:, :Dq], H, dh, S, cos, sin, inverse=True)
-            ops.rope_(dqkv[:, Dq: Dq + Dkv], Hkv, dh, S, cos, sin, inverse=True)
+            ops.rope_(dqkv[:, : Dq + Dkv], H + Hkv, dh, S, cos, sin, inverse=True)
             dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp["sv_qkv"])
             dx = ops.rmsnorm_bwd(dxn1, kp["x"], Lw["ln1"], kp["rstd1"], dres=dx2)
             sv["layers"][li] = None
