@@ -313,14 +313,16 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnP p) {
   float* sLseB = reinterpret_cast<float*>(sdS + BN * SPITCH);  // 2 stages of lse (log2 domain) ...
   float* sDeltaB = sLseB + 2 * BQ;                             // ... and delta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int k0 = blockIdx.x * BN;
+  // grid = (heads, batch, key blocks): CTAs are dispatched x-fastest, so all CTAs of key block 0 start first.  With a causal mask
+  // key block j only meets the query rows >= 64 j: heaviest work first (LPT) trims the tail of the 3-wave grid.
+  const int b = blockIdx.y;
+  const int k0 = blockIdx.z * BN;
   // split_heads: one CTA per (key block, Q head) writing per-head dK/dV partials (more parallelism, shorter critical path);
   // otherwise one CTA per (key block, KV head) looping over the heads of its group with dK/dV kept in registers
   const bool split_heads = p.dkv_part != nullptr;
   const int group_all = p.hq / p.hkv;
-  const int hk = split_heads ? static_cast<int>(blockIdx.y) / group_all : static_cast<int>(blockIdx.y);
-  const int h_first = split_heads ? static_cast<int>(blockIdx.y) : hk * group_all;
+  const int hk = split_heads ? static_cast<int>(blockIdx.x) / group_all : static_cast<int>(blockIdx.x);
+  const int h_first = split_heads ? static_cast<int>(blockIdx.x) : hk * group_all;
   const int group = split_heads ? 1 : group_all;
   const float scale_log2 = p.scale * kLog2e;
 
@@ -606,7 +608,7 @@ static int launch_bwd(const AttnP& p, cudaStream_t st) {
     cudaFuncSetAttribute(attn_bwd_kernel<DH, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     set = true;
   }
-  dim3 grid(static_cast<unsigned>(ceil_div(p.sk, 64)), p.dkv_part != nullptr ? p.hq : p.hkv, p.batch);
+  dim3 grid(p.dkv_part != nullptr ? p.hq : p.hkv, p.batch, static_cast<unsigned>(ceil_div(p.sk, 64)));
   launch_pdl(attn_bwd_kernel<DH, BQ>, grid, 128, SMEM, st, p);
   SLAM_LAUNCH_CHECK("slam_attn_bwd");
   return 0;

@@ -105,9 +105,12 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* s_maskbits = tmem_slot + 4;               // [FA_KST][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // grid = (heads, batch, query tiles), dispatched x-fastest: with a causal mask the LAST query tile meets the most key tiles,
+  // so the tile index is reversed and the heaviest CTAs start first (LPT; the decoder grid is 3.5 uneven waves)
+  const int h = blockIdx.x, b = blockIdx.y;
   const int hk = h / (p.hq / p.hkv);
-  const int q0 = blockIdx.x * FA_BM;
+  const int q_tile = (MASKED && p.causal) ? static_cast<int>(gridDim.z - 1 - blockIdx.z) : static_cast<int>(blockIdx.z);
+  const int q0 = q_tile * FA_BM;
   int n_tiles = (p.sk + FA_BN - 1) / FA_BN;
   if (MASKED && p.causal) n_tiles = min(n_tiles, (q0 + FA_BM + FA_BN - 1) / FA_BN);   // tiles above the diagonal never contribute
   const bool has_mask = MASKED && p.key_mask != nullptr;
@@ -441,7 +444,7 @@ int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
   p.ldo = a->ldo;
   p.lse = a->lse;
   p.key_mask = a->key_mask;
-  dim3 grid(static_cast<unsigned>(ceil_div(a->sq, FA_BM)), a->hq, a->batch);
+  dim3 grid(a->hq, a->batch, static_cast<unsigned>(ceil_div(a->sq, FA_BM)));
   const bool masked = a->causal || a->key_mask != nullptr || a->lse != nullptr;
   if (a->dh == 64) return masked ? fa_launch<64, true>(tq, tk, tv, p, grid, st) : fa_launch<64, false>(tq, tk, tv, p, grid, st);
   return masked ? fa_launch<128, true>(tq, tk, tv, p, grid, st) : fa_launch<128, false>(tq, tk, tv, p, grid, st);
