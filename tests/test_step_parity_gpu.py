@@ -176,3 +176,45 @@ def test_golden_fixture_matches_engine():
         assert abs(gk.norm().item() - norm) / max(norm, 1e-12) < 3e-2, k
         if norm > 1e-4:
             assert cosine(gk.flatten()[: head.numel()], head) > 0.98, k
+
+
+def test_full_size_c3_properties():
+    """BASELINE config 3 at FULL size (Whisper-large-v3 + Llama-3-8B, LoRA r=16 on q/v, 4 x 30 s, S = 401) - far beyond what the CPU
+    oracle finishes in a test, so checked through size-independent properties of the step:
+      * at initialisation-scale random weights the loss is that of a near-uniform predictor: |loss - ln V| small;
+      * repeatability: the same batch twice gives the same loss (fp32 atomics only reorder sums) and the same gradient direction;
+      * permutation of the utterances inside the batch changes neither the mean loss nor the summed gradient;
+      * the per-utterance losses of single-utterance steps average to the batch loss (every utterance has the same number of labels);
+      * one AdamW step with lr > 0 lowers the loss on the same batch."""
+    import math
+    import bench
+    from slam_llm_b200 import config as C
+    from slam_llm_b200.engine import SlamStepB200
+    wl = bench.WORKLOADS["c3"]
+    enc, llm = C.WHISPER[wl["enc"]], C.LLM[wl["llm"]]
+    eng = SlamStepB200(enc, llm, C.LoraCfg(wl["r"], wl["alpha"], tuple(wl["targets"])), C.ProjCfg("linear", 5, 2048), device="cuda:0", seed=42,
+                       lora_b_std=0.02)
+    host, S = bench.make_batch(wl, llm.vocab, seed=7)
+    assert S == 401
+    batch = to_dev(host)
+
+    def fwd_bwd(b):
+        loss, acc = eng.forward(b, train=True)[:2]
+        eng.micro_steps = 0
+        eng.backward(None)
+        return float(loss), eng.arena.grad.clone()
+
+    loss1, g1 = fwd_bwd(batch)
+    assert abs(loss1 - math.log(llm.vocab)) < 2.5, loss1                     # ln(128256) = 11.76; hidden-state scale shifts it a little
+    loss2, g2 = fwd_bwd(batch)
+    assert abs(loss1 - loss2) <= 1e-4 * abs(loss1) and cosine(g1, g2) > 0.9999
+    perm = torch.tensor([2, 0, 3, 1], device="cuda")
+    loss_p, g_p = fwd_bwd({k: v[perm] for k, v in batch.items()})
+    assert abs(loss_p - loss1) <= 2e-3 * abs(loss1), (loss_p, loss1)
+    assert cosine(g_p, g1) > 0.995 and rel_l2(g_p, g1) < 5e-2
+    singles = [float(eng.forward({k: v[i:i + 1] for k, v in batch.items()}, train=False)[0]) for i in range(4)]
+    assert abs(sum(singles) / 4 - loss1) <= 3e-3 * abs(loss1), (singles, loss1)
+    fwd_bwd(batch)
+    eng.optimizer_step(lr=1e-3, weight_decay=0.0)
+    loss_after = float(eng.forward(batch, train=False)[0])
+    assert loss_after < loss1, (loss_after, loss1)
