@@ -618,6 +618,7 @@ static int launch_bwd(const AttnP& p, cudaStream_t st) {
 
 namespace slam {
 int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st);   // fmha_tc.cu: 0 = launched, 1 = shape not handled, else error
+int fmha_bwd_tc_try(const slam_attn_args* a, cudaStream_t st);   // same contract; needs delta computed and dq_accum zeroed
 }
 
 extern "C" int slam_attn_fwd(const slam_attn_args* a, void* stream) {
@@ -659,7 +660,12 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
   const int total_warps = p.batch * p.sq * p.hq;
   launch_pdl(attn_delta_kernel, static_cast<unsigned>(ceil_div(total_warps, 8)), 256, 0, st, p, a->dh);
   SLAM_LAUNCH_CHECK("slam_attn_bwd.delta");
-  rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
+  static const bool use_tc = []() {
+    const char* e = getenv("SLAM_ATTN_BWD_TC");
+    return e == nullptr || e[0] != '0';
+  }();
+  rc = use_tc ? fmha_bwd_tc_try(a, st) : 1;           // tcgen05 / TMEM kernel for the Llama decoder shape (dh = 128)
+  if (rc == 1) rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
   if (rc != 0) return rc;
   if (p.dkv_part != nullptr) {
     const long long krows = static_cast<long long>(p.batch) * p.sk;

@@ -195,6 +195,16 @@ __device__ __forceinline__ void umma_kblock_1(uint32_t d_tmem, uint32_t a_lo, ui
       "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
       : "memory");
 }
+// same with an MN-major B operand (rows of the shared tile run along K): 16 K-rows = two 8-row groups = 2048 B per step
+__device__ __forceinline__ void umma_kblock_mnb(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, lead;\n\t.reg .b64 da, db;\n\t.reg .b32 alo, blo, dd;\n\t"
+      "elect.sync _|lead, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      SLAM_UMMA_STEP(1, 0, 0, 0, "p") SLAM_UMMA_STEP(1, 0, 2, 128, "1") SLAM_UMMA_STEP(1, 0, 4, 256, "1") SLAM_UMMA_STEP(1, 0, 6, 384, "1")
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
+      : "memory");
+}
 // CTA-pair variant (cta_group::2, leader CTA only)
 __device__ __forceinline__ void umma_kblock_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

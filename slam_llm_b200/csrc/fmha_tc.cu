@@ -4,7 +4,7 @@
 //
 // One CTA = 128 query rows of one (batch, head); the key/value sequence is walked in tiles of 128 keys.
 //   warp 0      TMA producer: Q tile once, then K (2-stage ring) and V tiles (128 x 64 bf16, 128B swizzle)
-//   warp 1      MMA issuer (one lane):  S_j = Q K_j^T  (M=128, N=128, K=64)  into one of two TMEM score buffers,
+//   warp 1      MMA issuer (whole warp):  S_j = Q K_j^T  (M=128, N=128, K=64)  into one of two TMEM score buffers,
 //                                       O  += P_j V_j  (M=128, N=64,  K=128) with P_j read from shared memory (K-major) and
 //                                       V_j used in place as an MN-major operand (no transposed copy of V)
 //               (warp 1 also allocates the CTA's 256 TMEM columns: 128 score + 64 output used; two CTAs share an SM)
@@ -186,25 +186,22 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (whole warp, warp-uniform operands: common.cuh)
     constexpr uint32_t idesc_s = fa_idesc(128, FA_BN, 0);      // S = Q K^T : both operands K-major
     constexpr uint32_t idesc_o = fa_idesc(128, 64, 1);         // O[:, 64 nb ..] += P V[:, 64 nb ..] : V is MN-major
+    constexpr uint32_t BLK = FA_TILE_BYTES >> 4;               // descriptor units between consecutive 64-wide blocks
+    const uint32_t lo_q = sw128_kmajor_desc_lo(smem_u32(sQ)), lo_k0 = sw128_kmajor_desc_lo(smem_u32(sK));
+    const uint32_t lo_v = sw128_kmajor_desc_lo(smem_u32(sV)), lo_p = sw128_kmajor_desc_lo(smem_u32(sP));
     auto issue_s = [&](int j) {
       const int ks = j % FA_KST;
       mbar_wait(&k_full[ks], (j / FA_KST) & 1u);
       mbar_wait(s_empty, (j & 1u) ^ 1u);                       // softmax of tile j-1 has the scores in registers
       tc_fence_after();
-      if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sQ + (k >> 2) * FA_TILE_BYTES)) + 2u * (k & 3);
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sK + (ks * NB + (k >> 2)) * FA_TILE_BYTES)) + 2u * (k & 3);
-          umma_bf16(tmem_base, a_desc, b_desc, idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(&k_empty[ks]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
+      for (uint32_t kb = 0; kb < static_cast<uint32_t>(NB); ++kb)   // K = dh in 64-wide blocks
+        umma_kblock_1(tmem_base, lo_q + kb * BLK, lo_k0 + (ks * NB + kb) * BLK, idesc_s, kb);
+      umma_commit_elect(smem_u32(&k_empty[ks]));
+      umma_commit_elect(smem_u32(s_full));
     };
     mbar_wait(q_full, 0);
     issue_s(0);
@@ -213,20 +210,14 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(p_full, j & 1u);
       mbar_wait(v_full, j & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      // K = 128 keys in two 64-key blocks of P (K-major, 16 KB apart); V block nb: 16 keys = two 8-row groups = 2048 B per step
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) {
-          // A = P: K-block k/4 (16 KB apart), 32 B per k-step inside it; B = V block nb: 16 keys = two 8-row groups = 2048 B per k-step
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2u * (k & 3);
+      for (uint32_t kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            umma_bf16(tmem_o + nb * 64, a_desc, make_sw128_mnmajor_desc(smem_u32(sV + nb * FA_TILE_BYTES)) + 128u * k, idesc_o,
-                      (j > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(v_empty);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
+        for (uint32_t nb = 0; nb < static_cast<uint32_t>(NB); ++nb)
+          umma_kblock_mnb(tmem_o + nb * 64, lo_p + kb * BLK, lo_v + nb * BLK + kb * 512u, idesc_o, (j > 0 || kb > 0) ? 1u : 0u);
+      umma_commit_elect(smem_u32(v_empty));
+      umma_commit_elect(smem_u32(pv_done));
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
@@ -448,6 +439,316 @@ int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
   const bool masked = a->causal || a->key_mask != nullptr || a->lse != nullptr;
   if (a->dh == 64) return masked ? fa_launch<64, true>(tq, tk, tv, p, grid, st) : fa_launch<64, false>(tq, tk, tv, p, grid, st);
   return masked ? fa_launch<128, true>(tq, tk, tv, p, grid, st) : fa_launch<128, false>(tq, tk, tv, p, grid, st);
+}
+
+// ================================================================================================== backward (dh = 128)
+// tcgen05 / TMEM flash-attention backward for the Llama decoder shape (replaces the mma.sync kernel of attention.cu there):
+// one CTA = 128 keys of one (batch, query head), looping over the 128-row query tiles that can see them.  Per tile pair
+//     S  = Q K^T              dP = dO V^T                      (both operands K-major, fp32 in TMEM)
+//     P  = exp2(S c - lse2)   dS = P o (dP - delta) * scale    (4 warps, thread = query row, straight from TMEM)
+//     dV += P^T dO            dK += dS^T Q                     (A = the TRANSPOSED bf16 tiles the threads write; B = dO / Q as MN-major)
+//     dQ  = dS K                                               (A = dS row-major; B = K as MN-major) -> fp32 red into dq_accum
+// TMEM (512 columns): dK [0,128) and dV [128,256) live across the whole loop; S [256,384) is reused for dQ once the softmax
+// warps have read it; dP [384,512).  Shared memory: K, V, Q, dO, P^T, dS^T, dS = 7 x 32 KB (Q / dO single-buffered).
+constexpr int FB_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 softmax / gradients
+constexpr int FB_SMEM = 7 * 2 * FA_TILE_BYTES + 256 + 1024;
+
+struct FmhaBwdParams {
+  int sq, sk, hq, hkv, causal;
+  float scale, scale_log2;
+  const float* lse;          // [B, Hq, Sq] natural log
+  const float* delta;        // [B, Hq, Sq] rowsum(dO o O)
+  const uint8_t* key_mask;   // [B, Sk] or NULL
+  float* dq_accum;           // [B, Sq, Hq, 128] fp32, zeroed
+  bf16* dk;                  // dk / dv rows: [B*Sk] x ld, head offset added by the kernel
+  bf16* dv;
+  long long lddk, lddv;
+  int head_stride_is_q;      // 1: dk/dv are per-QUERY-head partials [B, Sk, Hq, 128] (GQA); 0: final [.., hkv, 128] buffers (hq == hkv)
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmDO, const FmhaBwdParams p) {
+  constexpr int DH = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int T2 = 2 * FA_TILE_BYTES;   // one 128 x 128 bf16 tile = two 64-wide blocks
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + T2;
+  uint8_t* sQ = sV + T2;
+  uint8_t* sdO = sQ + T2;
+  uint8_t* sPt = sdO + T2;                // [key][q]  (K-major A operand with K = query rows)
+  uint8_t* sdSt = sPt + T2;               // [key][q]
+  uint8_t* sdS = sdSt + T2;               // [q][key]  (K-major A operand with K = keys)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + T2);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* qdo_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* dp_full = bars + 4;
+  uint64_t* pds_ready = bars + 5;
+  uint64_t* dq_full = bars + 6;
+  uint64_t* dq_drained = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hk = h / (p.hq / p.hkv);
+  const int j = blockIdx.z;                                  // key tile (LPT: with a causal mask tile 0 has the most work and starts first)
+  const int k0 = j * 128;
+  const int nq = (p.sq + 127) / 128;
+  const int i_start = p.causal ? j : 0;
+  const int n_it = nq - i_start;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(pds_ready, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_drained, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_dk = tmem_base, t_dv = tmem_base + 128, t_s = tmem_base + 256, t_dp = tmem_base + 384;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * T2);
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        tma_load_2d(sK + nb * FA_TILE_BYTES, &tmK, kv_full, hk * DH + nb * 64, b * p.sk + k0);
+        tma_load_2d(sV + nb * FA_TILE_BYTES, &tmV, kv_full, hk * DH + nb * 64, b * p.sk + k0);
+      }
+    }
+    for (int it = 0; it < n_it; ++it) {
+      if (it > 0) mbar_wait(qdo_empty, (it - 1) & 1u);       // the MMAs that read the previous Q / dO tiles have completed
+      if (lane == 0) {
+        const int q0 = (i_start + it) * 128;
+        mbar_arrive_expect_tx(qdo_full, 2 * T2);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          tma_load_2d(sQ + nb * FA_TILE_BYTES, &tmQ, qdo_full, h * DH + nb * 64, b * p.sq + q0);
+          tma_load_2d(sdO + nb * FA_TILE_BYTES, &tmDO, qdo_full, h * DH + nb * 64, b * p.sq + q0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, warp-uniform operands: common.cuh)
+    constexpr uint32_t idesc_kk = fa_idesc(128, 128, 0);     // A, B K-major
+    constexpr uint32_t idesc_mn = fa_idesc(128, 64, 1);      // A K-major, B MN-major, 64 output columns per instruction
+    const uint32_t lo_q = sw128_kmajor_desc_lo(smem_u32(sQ)), lo_k = sw128_kmajor_desc_lo(smem_u32(sK)), lo_v = sw128_kmajor_desc_lo(smem_u32(sV));
+    const uint32_t lo_do = sw128_kmajor_desc_lo(smem_u32(sdO)), lo_pt = sw128_kmajor_desc_lo(smem_u32(sPt));
+    const uint32_t lo_dst = sw128_kmajor_desc_lo(smem_u32(sdSt)), lo_ds = sw128_kmajor_desc_lo(smem_u32(sdS));
+    constexpr uint32_t BLK = FA_TILE_BYTES >> 4;             // descriptor units between the two 64-wide blocks of a tile
+    mbar_wait(kv_full, 0);
+    for (int it = 0; it < n_it; ++it) {
+      mbar_wait(qdo_full, it & 1u);
+      if (it > 0) mbar_wait(dq_drained, (it - 1) & 1u);      // dQ of the previous tile has left the columns S is written to
+      tc_fence_after();
+      umma_kblock_1(t_s, lo_q, lo_k, idesc_kk, 0u);          // S = Q K^T   (K = dh: two 64-wide blocks)
+      umma_kblock_1(t_s, lo_q + BLK, lo_k + BLK, idesc_kk, 1u);
+      umma_commit_elect(smem_u32(s_full));
+      umma_kblock_1(t_dp, lo_do, lo_v, idesc_kk, 0u);        // dP = dO V^T
+      umma_kblock_1(t_dp, lo_do + BLK, lo_v + BLK, idesc_kk, 1u);
+      umma_commit_elect(smem_u32(dp_full));
+      mbar_wait(pds_ready, it & 1u);
+      tc_fence_after();
+      // K dimension = 128 query rows (dV, dK) resp. 128 keys (dQ): block kb = rows 64 kb .. 64 kb + 63 of the MN-major B tile (+8192 B)
+#pragma unroll
+      for (uint32_t kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (uint32_t nb = 0; nb < 2; ++nb) {
+          umma_kblock_mnb(t_dv + nb * 64, lo_pt + kb * BLK, lo_do + nb * BLK + kb * 512u, idesc_mn, (it > 0 || kb > 0) ? 1u : 0u);   // dV += P^T dO
+          umma_kblock_mnb(t_dk + nb * 64, lo_dst + kb * BLK, lo_q + nb * BLK + kb * 512u, idesc_mn, (it > 0 || kb > 0) ? 1u : 0u);  // dK += dS^T Q
+          umma_kblock_mnb(t_s + nb * 64, lo_ds + kb * BLK, lo_k + nb * BLK + kb * 512u, idesc_mn, kb);                              // dQ = dS K
+        }
+      }
+      umma_commit_elect(smem_u32(qdo_empty));
+      umma_commit_elect(smem_u32(dq_full));
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax / gradient warps (thread = query row resp. key row)
+    const int qd = warp & 3;
+    const int rl = qd * 32 + lane;                           // row inside the tile = TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    // key validity of this CTA's 128 keys as four 32-bit words (bit e of word w = key k0 + 32 w + e may be attended)
+    uint32_t kbits[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int key = k0 + 32 * w + lane;
+      const bool ok = key < p.sk && (p.key_mask == nullptr || p.key_mask[static_cast<long long>(b) * p.sk + key] != 0);
+      kbits[w] = __ballot_sync(0xffffffffu, ok);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      const int row = q0 + rl;
+      const bool row_ok = row < p.sq;
+      const long long stat = (static_cast<long long>(b) * p.hq + h) * p.sq + (row_ok ? row : 0);
+      const float lse2 = row_ok ? p.lse[stat] * 1.4426950408889634f : 0.0f;
+      const float dlt = row_ok ? p.delta[stat] : 0.0f;
+      mbar_wait(s_full, it & 1u);
+      mbar_wait(dp_full, it & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(t_s + lane_base + c * 32, sv);
+        tmem_ld_32x32(t_dp + lane_base + c * 32, dv);
+        tmem_ld_wait();
+        uint32_t valid = row_ok ? kbits[c] : 0u;
+        if (p.causal) {                                      // keys after the query are masked
+          const int lim = row - (k0 + c * 32);               // key offsets 0 .. lim inside this chunk stay
+          valid &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : (0xffffffffu >> (31 - lim)));
+        }
+        uint32_t pds[16];                                    // dS row chunk, packed bf16 pairs
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ((valid >> e) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2)) : 0.0f;
+          const float p1 = ((valid >> (e + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2)) : 0.0f;
+          const float d0 = p0 * (__uint_as_float(dv[e]) - dlt) * p.scale;
+          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - dlt) * p.scale;
+          const uint32_t pp = pack_bf16x2(p0, p1), dd = pack_bf16x2(d0, d1);
+          pds[e >> 1] = dd;
+          // transposed stores: element (key, q = rl) of the [key][q] tiles; 64-q blocks, 16-byte chunks XOR-swizzled by (key % 8)
+          const int key_a = c * 32 + e, key_b = key_a + 1;
+          const int base = (rl >> 6) * FA_TILE_BYTES + (rl & 7) * 2;
+          const int qchunk = (rl & 63) >> 3;
+          const int off_a = base + key_a * 128 + ((qchunk ^ (key_a & 7)) << 4);
+          const int off_b = base + key_b * 128 + ((qchunk ^ (key_b & 7)) << 4);
+          *reinterpret_cast<uint16_t*>(sPt + off_a) = static_cast<uint16_t>(pp & 0xffffu);
+          *reinterpret_cast<uint16_t*>(sPt + off_b) = static_cast<uint16_t>(pp >> 16);
+          *reinterpret_cast<uint16_t*>(sdSt + off_a) = static_cast<uint16_t>(dd & 0xffffu);
+          *reinterpret_cast<uint16_t*>(sdSt + off_b) = static_cast<uint16_t>(dd >> 16);
+        }
+        // row-major dS: 32 keys = 4 chunks of 16 B inside the 64-key block c / 2, XOR-swizzled by (row % 8)
+        uint8_t* drow = sdS + (c >> 1) * FA_TILE_BYTES + rl * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(drow + ((((c & 1) * 4 + q4) ^ (rl & 7)) << 4)) = make_uint4(pds[4 * q4], pds[4 * q4 + 1], pds[4 * q4 + 2], pds[4 * q4 + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+      // dQ of this tile pair: fp32 reduction into the accumulator every key tile of the row adds to
+      mbar_wait(dq_full, it & 1u);
+      tc_fence_after();
+      float* dqrow = p.dq_accum + ((static_cast<long long>(b) * p.sq + (row_ok ? row : 0)) * p.hq + h) * DH;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + lane_base + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {                                        // 16-byte vector reductions: the scalar form is bound by L2 atomic operations
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqrow + c * 32 + e), "f"(__uint_as_float(r[e])),
+                         "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_drained);
+    }
+    // dK / dV of this (key tile, query head): TMEM lane = key row -> bf16 rows
+    const int key = k0 + rl;
+    const int hcol = p.head_stride_is_q ? h : hk;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      bf16* dst = (which == 0 ? p.dk : p.dv) + (static_cast<long long>(b) * p.sk + (key < p.sk ? key : 0)) * (which == 0 ? p.lddk : p.lddv) + hcol * DH;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32((which == 0 ? t_dk : t_dv) + lane_base + c * 32, r);
+        tmem_ld_wait();
+        if (key < p.sk) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * g) =
+                make_uint4(pack_bf16x2(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                           pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])), pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Returns 1 if the shape is not handled (caller falls through to the mma.sync backward), 0 when launched.  Expects delta computed and
+// dq_accum zeroed on the stream (slam_attn_bwd does both); dkv_part non-NULL means per-query-head dK/dV partials (GQA).
+int fmha_bwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
+  if (a->dh != 128 || a->sq != a->sk || a->sk < 64 || a->hkv <= 0 || a->hq % a->hkv != 0 || a->lse == nullptr) return 1;
+  if (a->hq != a->hkv && a->dkv_part == nullptr) return 1;
+  if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->k) & 15) || (reinterpret_cast<uintptr_t>(a->v) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->dout) & 15))
+    return 1;
+  CUtensorMap tq, tk, tv, tdo;
+  const long long rows_q = static_cast<long long>(a->batch) * a->sq, rows_k = static_cast<long long>(a->batch) * a->sk;
+  int rc;
+  if ((rc = fa_make_tmap(&tq, a->q, rows_q, static_cast<long long>(a->hq) * a->dh, a->ldq)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tk, a->k, rows_k, static_cast<long long>(a->hkv) * a->dh, a->ldk)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tv, a->v, rows_k, static_cast<long long>(a->hkv) * a->dh, a->ldv)) != 0) return rc;
+  if ((rc = fa_make_tmap(&tdo, a->dout, rows_q, static_cast<long long>(a->hq) * a->dh, a->lddo)) != 0) return rc;
+  FmhaBwdParams p;
+  p.sq = a->sq;
+  p.sk = a->sk;
+  p.hq = a->hq;
+  p.hkv = a->hkv;
+  p.causal = a->causal;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.lse = a->lse;
+  p.delta = a->delta;
+  p.key_mask = a->key_mask;
+  p.dq_accum = a->dq_accum;
+  if (a->dkv_part != nullptr) {
+    p.head_stride_is_q = 1;
+    p.dk = reinterpret_cast<bf16*>(a->dkv_part);
+    p.dv = p.dk + rows_k * a->hq * a->dh;
+    p.lddk = p.lddv = static_cast<long long>(a->hq) * a->dh;
+  } else {
+    p.head_stride_is_q = 0;
+    p.dk = reinterpret_cast<bf16*>(a->dk);
+    p.dv = reinterpret_cast<bf16*>(a->dv);
+    p.lddk = a->lddk;
+    p.lddv = a->lddv;
+  }
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fmha_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+    if (e != cudaSuccess) {
+      set_error("fmha bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    set = true;
+  }
+  dim3 grid(a->hq, a->batch, static_cast<unsigned>(ceil_div(a->sk, 128)));
+  launch_pdl(fmha_bwd_tc_kernel, grid, FB_THREADS, FB_SMEM, st, tq, tk, tv, tdo, p);
+  SLAM_LAUNCH_CHECK("slam_attn_bwd.tcgen05");
+  return 0;
 }
 
 }  // namespace slam

