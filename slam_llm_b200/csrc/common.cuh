@@ -205,6 +205,20 @@ __device__ __forceinline__ void umma_kblock_mnb(uint32_t d_tmem, uint32_t a_lo, 
       "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
       : "memory");
 }
+// A AND B MN-major (both tiles stored with their K dimension along the rows): +2048 B per 16-row K step on both operands
+__device__ __forceinline__ void umma_kblock_mna_mnb(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, lead;\n\t.reg .b64 da, db;\n\t.reg .b32 alo, blo, dd;\n\t"
+      "elect.sync _|lead, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      SLAM_UMMA_STEP(1, 0, 0, 0, "p") SLAM_UMMA_STEP(1, 0, 128, 128, "1") SLAM_UMMA_STEP(1, 0, 256, 256, "1") SLAM_UMMA_STEP(1, 0, 384, 384, "1")
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_KMAJOR_DESC_HI)
+      : "memory");
+}
+// low descriptor word of an MN-major SW128 tile made of 64-element MN blocks `lbo_bytes` apart (8-row K groups 1024 B apart)
+__device__ __forceinline__ uint32_t sw128_mnmajor_desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
 // CTA-pair variant (cta_group::2, leader CTA only)
 __device__ __forceinline__ void umma_kblock_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

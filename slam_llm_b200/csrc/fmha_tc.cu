@@ -445,11 +445,12 @@ int fmha_fwd_tc_try(const slam_attn_args* a, cudaStream_t st) {
 // tcgen05 / TMEM flash-attention backward for the Llama decoder shape (replaces the mma.sync kernel of attention.cu there):
 // one CTA = 128 keys of one (batch, query head), looping over the 128-row query tiles that can see them.  Per tile pair
 //     S  = Q K^T              dP = dO V^T                      (both operands K-major, fp32 in TMEM)
-//     P  = exp2(S c - lse2)   dS = P o (dP - delta) * scale    (4 warps, thread = query row, straight from TMEM)
-//     dV += P^T dO            dK += dS^T Q                     (A = the TRANSPOSED bf16 tiles the threads write; B = dO / Q as MN-major)
-//     dQ  = dS K                                               (A = dS row-major; B = K as MN-major) -> fp32 red into dq_accum
+//     P  = exp2(S c - lse2)   dS = P o (dP - delta) * scale    (4 warps, thread = query row, straight from TMEM; bf16 tiles [q][key])
+//     dV += P^T dO            dK += dS^T Q                     (A = P / dS read as MN-major operands, B = dO / Q as MN-major: no transposes)
+//     dQ  = dS K                                               (A = dS K-major; B = K as MN-major) -> fp32 vector reductions into dq_accum
 // TMEM (512 columns): dK [0,128) and dV [128,256) live across the whole loop; S [256,384) is reused for dQ once the softmax
-// warps have read it; dP [384,512).  Shared memory: K, V, Q, dO, P^T, dS^T, dS = 7 x 32 KB (Q / dO single-buffered).
+// warps have read it; dP [384,512).  Shared memory: K, V, 2 x Q (double-buffered), dO, P, dS = 7 x 32 KB; the next dO is requested
+// as soon as the dV MMAs (its last readers) have completed.
 constexpr int FB_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 softmax / gradients
 constexpr int FB_SMEM = 7 * 2 * FA_TILE_BYTES + 256 + 1024;
 
@@ -475,21 +476,22 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int T2 = 2 * FA_TILE_BYTES;   // one 128 x 128 bf16 tile = two 64-wide blocks
   uint8_t* sK = smem;
   uint8_t* sV = sK + T2;
-  uint8_t* sQ = sV + T2;
-  uint8_t* sdO = sQ + T2;
-  uint8_t* sPt = sdO + T2;                // [key][q]  (K-major A operand with K = query rows)
-  uint8_t* sdSt = sPt + T2;               // [key][q]
-  uint8_t* sdS = sdSt + T2;               // [q][key]  (K-major A operand with K = keys)
+  uint8_t* sQ = sV + T2;                  // 2 stages
+  uint8_t* sdO = sQ + 2 * T2;
+  uint8_t* sP = sdO + T2;                 // [q][key]: K-major over keys (dQ), MN-major over keys with K = query rows (dV, dK)
+  uint8_t* sdS = sP + T2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + T2);
   uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;
-  uint64_t* qdo_empty = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* dp_full = bars + 4;
-  uint64_t* pds_ready = bars + 5;
-  uint64_t* dq_full = bars + 6;
-  uint64_t* dq_drained = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars + 1;            // [2]
+  uint64_t* q_empty = bars + 3;           // [2]
+  uint64_t* do_full = bars + 5;
+  uint64_t* do_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* dp_full = bars + 8;
+  uint64_t* pds_ready = bars + 9;
+  uint64_t* dq_full = bars + 10;
+  uint64_t* dq_drained = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -507,8 +509,12 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
     mbar_init(pds_ready, 4);
@@ -538,50 +544,66 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     for (int it = 0; it < n_it; ++it) {
-      if (it > 0) mbar_wait(qdo_empty, (it - 1) & 1u);       // the MMAs that read the previous Q / dO tiles have completed
+      const int q0 = (i_start + it) * 128;
+      const int qs = it & 1;
+      if (it >= 2) mbar_wait(&q_empty[qs], ((it - 2) >> 1) & 1u);   // dK MMAs of iteration it - 2 (last readers of this Q stage) completed
       if (lane == 0) {
-        const int q0 = (i_start + it) * 128;
-        mbar_arrive_expect_tx(qdo_full, 2 * T2);
+        mbar_arrive_expect_tx(&q_full[qs], T2);
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          tma_load_2d(sQ + nb * FA_TILE_BYTES, &tmQ, qdo_full, h * DH + nb * 64, b * p.sq + q0);
-          tma_load_2d(sdO + nb * FA_TILE_BYTES, &tmDO, qdo_full, h * DH + nb * 64, b * p.sq + q0);
-        }
+        for (int nb = 0; nb < 2; ++nb) tma_load_2d(sQ + qs * T2 + nb * FA_TILE_BYTES, &tmQ, &q_full[qs], h * DH + nb * 64, b * p.sq + q0);
+      }
+      if (it >= 1) mbar_wait(do_empty, (it - 1) & 1u);               // dV MMAs of the previous iteration completed
+      if (lane == 0) {
+        mbar_arrive_expect_tx(do_full, T2);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) tma_load_2d(sdO + nb * FA_TILE_BYTES, &tmDO, do_full, h * DH + nb * 64, b * p.sq + q0);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, warp-uniform operands: common.cuh)
-    constexpr uint32_t idesc_kk = fa_idesc(128, 128, 0);     // A, B K-major
-    constexpr uint32_t idesc_mn = fa_idesc(128, 64, 1);      // A K-major, B MN-major, 64 output columns per instruction
-    const uint32_t lo_q = sw128_kmajor_desc_lo(smem_u32(sQ)), lo_k = sw128_kmajor_desc_lo(smem_u32(sK)), lo_v = sw128_kmajor_desc_lo(smem_u32(sV));
-    const uint32_t lo_do = sw128_kmajor_desc_lo(smem_u32(sdO)), lo_pt = sw128_kmajor_desc_lo(smem_u32(sPt));
-    const uint32_t lo_dst = sw128_kmajor_desc_lo(smem_u32(sdSt)), lo_ds = sw128_kmajor_desc_lo(smem_u32(sdS));
-    constexpr uint32_t BLK = FA_TILE_BYTES >> 4;             // descriptor units between the two 64-wide blocks of a tile
+    constexpr uint32_t idesc_kk = fa_idesc(128, 128, 0);               // A, B K-major
+    constexpr uint32_t idesc_kmn = fa_idesc(128, 64, 1);               // A K-major, B MN-major, 64 output columns per instruction
+    constexpr uint32_t idesc_mnmn = fa_idesc(128, 64, 1) | (1u << 15); // A and B MN-major
+    constexpr uint32_t BLK = FA_TILE_BYTES >> 4;                       // descriptor units between the two 64-wide blocks of a tile
+    const uint32_t lo_k = sw128_kmajor_desc_lo(smem_u32(sK)), lo_v = sw128_kmajor_desc_lo(smem_u32(sV));
+    const uint32_t lo_do = sw128_kmajor_desc_lo(smem_u32(sdO)), lo_ds = sw128_kmajor_desc_lo(smem_u32(sdS));
+    // P / dS as MN-major A operands (M = keys): two 64-key blocks FA_TILE_BYTES apart, K = query rows (128 B apart)
+    const uint32_t mn_p = sw128_mnmajor_desc_lo(smem_u32(sP), FA_TILE_BYTES), mn_ds = sw128_mnmajor_desc_lo(smem_u32(sdS), FA_TILE_BYTES);
     mbar_wait(kv_full, 0);
     for (int it = 0; it < n_it; ++it) {
-      mbar_wait(qdo_full, it & 1u);
+      const uint32_t lo_q = sw128_kmajor_desc_lo(smem_u32(sQ + (it & 1) * T2));
+      mbar_wait(&q_full[it & 1], (it >> 1) & 1u);
       if (it > 0) mbar_wait(dq_drained, (it - 1) & 1u);      // dQ of the previous tile has left the columns S is written to
       tc_fence_after();
       umma_kblock_1(t_s, lo_q, lo_k, idesc_kk, 0u);          // S = Q K^T   (K = dh: two 64-wide blocks)
       umma_kblock_1(t_s, lo_q + BLK, lo_k + BLK, idesc_kk, 1u);
       umma_commit_elect(smem_u32(s_full));
+      mbar_wait(do_full, it & 1u);
+      tc_fence_after();
       umma_kblock_1(t_dp, lo_do, lo_v, idesc_kk, 0u);        // dP = dO V^T
       umma_kblock_1(t_dp, lo_do + BLK, lo_v + BLK, idesc_kk, 1u);
       umma_commit_elect(smem_u32(dp_full));
       mbar_wait(pds_ready, it & 1u);
       tc_fence_after();
-      // K dimension = 128 query rows (dV, dK) resp. 128 keys (dQ): block kb = rows 64 kb .. 64 kb + 63 of the MN-major B tile (+8192 B)
+      // K dimension = 128 query rows (dV, dK) resp. 128 keys (dQ); kb = its 64-row halves (+8192 B on the operands whose rows are K)
 #pragma unroll
-      for (uint32_t kb = 0; kb < 2; ++kb) {
+      for (uint32_t kb = 0; kb < 2; ++kb)
 #pragma unroll
-        for (uint32_t nb = 0; nb < 2; ++nb) {
-          umma_kblock_mnb(t_dv + nb * 64, lo_pt + kb * BLK, lo_do + nb * BLK + kb * 512u, idesc_mn, (it > 0 || kb > 0) ? 1u : 0u);   // dV += P^T dO
-          umma_kblock_mnb(t_dk + nb * 64, lo_dst + kb * BLK, lo_q + nb * BLK + kb * 512u, idesc_mn, (it > 0 || kb > 0) ? 1u : 0u);  // dK += dS^T Q
-          umma_kblock_mnb(t_s + nb * 64, lo_ds + kb * BLK, lo_k + nb * BLK + kb * 512u, idesc_mn, kb);                              // dQ = dS K
-        }
-      }
-      umma_commit_elect(smem_u32(qdo_empty));
+        for (uint32_t nb = 0; nb < 2; ++nb)                  // dV += P^T dO
+          umma_kblock_mna_mnb(t_dv + nb * 64, mn_p + kb * 512u, lo_do + nb * BLK + kb * 512u, idesc_mnmn, (it > 0 || kb > 0) ? 1u : 0u);
+      umma_commit_elect(smem_u32(do_empty));                 // dO may be replaced by the next tile's
+#pragma unroll
+      for (uint32_t kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (uint32_t nb = 0; nb < 2; ++nb)                  // dK += dS^T Q
+          umma_kblock_mna_mnb(t_dk + nb * 64, mn_ds + kb * 512u, lo_q + nb * BLK + kb * 512u, idesc_mnmn, (it > 0 || kb > 0) ? 1u : 0u);
+      umma_commit_elect(smem_u32(&q_empty[it & 1]));
+#pragma unroll
+      for (uint32_t kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (uint32_t nb = 0; nb < 2; ++nb)                  // dQ = dS K   (into the columns S occupied)
+          umma_kblock_mnb(t_s + nb * 64, lo_ds + kb * BLK, lo_k + nb * BLK + kb * 512u, idesc_kmn, kb);
       umma_commit_elect(smem_u32(dq_full));
     }
   } else if (warp >= 4) {
@@ -618,31 +640,22 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int lim = row - (k0 + c * 32);               // key offsets 0 .. lim inside this chunk stay
           valid &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : (0xffffffffu >> (31 - lim)));
         }
-        uint32_t pds[16];                                    // dS row chunk, packed bf16 pairs
+        uint32_t pp[16], pds[16];                            // P and dS row chunks, packed bf16 pairs
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float p0 = ((valid >> e) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2)) : 0.0f;
           const float p1 = ((valid >> (e + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2)) : 0.0f;
-          const float d0 = p0 * (__uint_as_float(dv[e]) - dlt) * p.scale;
-          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - dlt) * p.scale;
-          const uint32_t pp = pack_bf16x2(p0, p1), dd = pack_bf16x2(d0, d1);
-          pds[e >> 1] = dd;
-          // transposed stores: element (key, q = rl) of the [key][q] tiles; 64-q blocks, 16-byte chunks XOR-swizzled by (key % 8)
-          const int key_a = c * 32 + e, key_b = key_a + 1;
-          const int base = (rl >> 6) * FA_TILE_BYTES + (rl & 7) * 2;
-          const int qchunk = (rl & 63) >> 3;
-          const int off_a = base + key_a * 128 + ((qchunk ^ (key_a & 7)) << 4);
-          const int off_b = base + key_b * 128 + ((qchunk ^ (key_b & 7)) << 4);
-          *reinterpret_cast<uint16_t*>(sPt + off_a) = static_cast<uint16_t>(pp & 0xffffu);
-          *reinterpret_cast<uint16_t*>(sPt + off_b) = static_cast<uint16_t>(pp >> 16);
-          *reinterpret_cast<uint16_t*>(sdSt + off_a) = static_cast<uint16_t>(dd & 0xffffu);
-          *reinterpret_cast<uint16_t*>(sdSt + off_b) = static_cast<uint16_t>(dd >> 16);
+          pp[e >> 1] = pack_bf16x2(p0, p1);
+          pds[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dlt) * p.scale, p1 * (__uint_as_float(dv[e + 1]) - dlt) * p.scale);
         }
-        // row-major dS: 32 keys = 4 chunks of 16 B inside the 64-key block c / 2, XOR-swizzled by (row % 8)
-        uint8_t* drow = sdS + (c >> 1) * FA_TILE_BYTES + rl * 128;
+        // row-major [q][key] tiles: 32 keys = 4 chunks of 16 B inside the 64-key block c / 2, XOR-swizzled by (row % 8)
+        const int roff = (c >> 1) * FA_TILE_BYTES + rl * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(drow + ((((c & 1) * 4 + q4) ^ (rl & 7)) << 4)) = make_uint4(pds[4 * q4], pds[4 * q4 + 1], pds[4 * q4 + 2], pds[4 * q4 + 3]);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int ch = (((c & 1) * 4 + q4) ^ (rl & 7)) << 4;
+          *reinterpret_cast<uint4*>(sP + roff + ch) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(sdS + roff + ch) = make_uint4(pds[4 * q4], pds[4 * q4 + 1], pds[4 * q4 + 2], pds[4 * q4 + 3]);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
