@@ -1,21 +1,22 @@
 // tcgen05 / TMEM / TMA GEMM core for the SLAM-LLM training step on B200 (sm_100a).
 //
-//   out[M,N] = act(alpha * (A·B^T + A2·B2^T) + bias) + residual
+//   out[M,N] = act(alpha * (A·B^T + A2·B2^T) + bias) + residual          (+ fused SwiGLU forward / backward epilogues)
 //
-// Design (one CTA per SM, persistent over output tiles, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of 128xBK (A) and BNxBK (B) bf16 tiles
-//               into a STAGES-deep 128B-swizzled shared-memory ring, completion on mbarriers;
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) with both operands
-//               read from shared memory through UMMA descriptors, fp32 accumulator in TMEM;
+// Design (one CTA per SM, persistent over output tiles, warp-specialised, 384 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of BLOCK_M x 64 (A) and BLOCK_N x 64 (B) bf16 k-blocks into a
+//               STAGES-deep 128B-swizzled shared-memory ring, completion on mbarriers;
+//   warp 1      MMA issuer: the whole warp runs the loop with warp-uniform operands, one elected lane issues the four
+//               tcgen05.mma (M=128, N=BLOCK_N, K=16) of a k-block back to back (see "warp-uniform issue helpers" in
+//               common.cuh: issuing from an `if (lane == 0)` branch made this warp the bottleneck of the kernel);
 //               tcgen05.commit releases ring slots / publishes the accumulator;
 //   warp 2      TMEM allocator (BLOCK_M=128: 2 accumulator stages so the epilogue of tile i overlaps tile i+1;
-//               BLOCK_M=256: two M=128 accumulators that SHARE every B tile — the mainloop is bound by the bytes one SM can
-//               keep in flight from L2 (~60 B/clk/SM measured), so 256x256 tiles need 1/3 less traffic per MMA cycle);
-//   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> alpha/bias/activation/residual ->
-//               16-byte global stores (bf16 or f32).
+//               BLOCK_M=256: two M=128 accumulators that share every B tile, single accumulator set);
+//   warps 4-11  epilogue (gemm_common.cuh): tcgen05.ld 32x32b -> math in the row layout -> bf16 transpose through shared
+//               memory -> 16-byte stores; two warps per TMEM lane quarter, interleaved 32-column chunks.
 // The K loop runs over TWO operand pairs back to back ("dual K segment"): the base weights and the
 // rank-padded LoRA pair, so y = xW^T + (alpha/r)(xA^T)B^T is produced in ONE accumulator tile
 // (reference: peft lora.Linear.forward called under models/slam_model.py:400).
+// gemm_2cta.cuh holds the CTA-pair (cta_group::2) variant; GemmSchedule (gemm_common.cuh) the tile order and the tail split.
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -28,9 +29,7 @@
 
 namespace slam {
 
-#ifndef SLAM_GEMM_PREFETCH
-#define SLAM_GEMM_PREFETCH 0   // L2 prefetch distance of the weight operand in k-blocks; measured on B200: 4/8/16 are ~10 % SLOWER than 0 (profiles/r01_exp_prefetch.log)
-#endif
+// (An L2 prefetch of the weight operand 4/8/16 k-blocks ahead measured ~10 % SLOWER than none: profiles/r01_exp_prefetch.log.)
 
 template <int BLOCK_M, int BLOCK_N>
 struct GemmCfg {
