@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SLAM_B200_ABI_VERSION 3
+#define SLAM_B200_ABI_VERSION 4
 
 int slam_abi_version(void);
 const char* slam_last_error(void);
@@ -83,9 +83,10 @@ int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
 int64_t slam_gemm_workspace_bytes(void);
 
 /* C[P,Q] (f32) = scale * sum_m A[m,P] * B[m,Q]   (thin weight-gradient product: P <= 64)
- * Used for LoRA dA / dB (peft lora.Linear backward) and bias gradients.  C is OVERWRITTEN. */
+ * Used for LoRA dA / dB (peft lora.Linear backward) and bias gradients.  accumulate = 0: C is OVERWRITTEN;
+ * accumulate != 0: the product is ADDED to C (the step zeroes its flat gradient buffer once instead of per product). */
 int slam_wgrad_thin(const void* a_bf16, int64_t lda, int32_t p, const void* b_bf16, int64_t ldb,
-                    int32_t q, int32_t m, float scale, float* c, int64_t ldc, void* stream);
+                    int32_t q, int32_t m, float scale, float* c, int64_t ldc, int32_t accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a1  log-mel front end.  whisper.pad_or_trim + whisper.log_mel_spectrogram(...).permute(1,0)

@@ -295,14 +295,16 @@ int slam_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets,
 }
 
 int slam_wgrad_thin(const void* a, int64_t lda, int32_t p, const void* b, int64_t ldb, int32_t q, int32_t m, float scale, float* c, int64_t ldc,
-                    void* stream) {
+                    int32_t accumulate, void* stream) {
   using namespace slam;
   SLAM_CHECK_ARG(p > 0 && p <= 64 && q > 0 && m > 0, "wgrad_thin: bad shape p=%d q=%d m=%d", p, q, m);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  long long zb = ceil_div(static_cast<long long>(p) * q, 256);
-  if (zb > 1184) zb = 1184;
-  launch_pdl(zero2d_kernel, static_cast<unsigned>(zb), 256, 0, st, c, ldc, p, q);
-  SLAM_LAUNCH_CHECK("slam_wgrad_thin.zero");
+  if (!accumulate) {   // the M-chunks of the product are merged with fp32 atomics: C starts from zero unless the caller accumulates
+    long long zb = ceil_div(static_cast<long long>(p) * q, 256);
+    if (zb > 1184) zb = 1184;
+    launch_pdl(zero2d_kernel, static_cast<unsigned>(zb), 256, 0, st, c, ldc, p, q);
+    SLAM_LAUNCH_CHECK("slam_wgrad_thin.zero");
+  }
   const bf16* ap = reinterpret_cast<const bf16*>(a);
   const bf16* bp = reinterpret_cast<const bf16*>(b);
   const bool aligned = p % 8 == 0 && q % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&

@@ -473,8 +473,8 @@ class LlamaLoRAB200:
             out_f = linear_shape(self.cfg, m)[0]
             gA = self.arena.view(self._pname(m, "A"), "grad")[li]
             gBt = self.arena.view(self._pname(m, "Bt"), "grad")[li]
-            ops.wgrad_thin(u[:, off: off + r], x_lora, gA)
-            ops.wgrad_thin(t[:, off: off + r], dy[:, col: col + out_f], gBt, scale=s)
+            ops.wgrad_thin(u[:, off: off + r], x_lora, gA, accumulate=True)          # (the flat gradient buffer was zeroed once: backward())
+            ops.wgrad_thin(t[:, off: off + r], dy[:, col: col + out_f], gBt, scale=s, accumulate=True)
         return dx
 
     # ---------------------------------------------------------------------------------------- forward
@@ -671,6 +671,7 @@ class SlamStepB200:
         self._ctx = None
         dev = self.device
         carry = self.arena.grad.clone() if self.micro_steps > 0 else None                 # gradient accumulation: kernels overwrite
+        self.arena.grad.zero_()                                                           # one memset: the LoRA wgrad products accumulate
         gs = (1.0 / c["nv"]) if grad_out is None else (grad_out.to(dev, F32).reshape(1) / c["nv"])
         gs = gs.contiguous()
         logits = c["logits"]

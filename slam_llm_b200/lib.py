@@ -66,7 +66,7 @@ _SIGS = {
     "slam_launch_count": [],
     "slam_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "slam_gemm_workspace_bytes": [],
-    "slam_wgrad_thin": [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp],
+    "slam_wgrad_thin": [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _i32, _vp],
     "slam_logmel": [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "slam_conv_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "slam_add_pos": [_vp, _vp, _i32, _i32, _i32, _vp],
@@ -122,8 +122,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.slam_abi_version() != 3:
-        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 3")
+    if lib.slam_abi_version() != 4:
+        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 4")
     _lib = lib
     return lib
 

@@ -144,14 +144,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     return out
 
 
-def wgrad_thin(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-    """out[P,Q] (f32) = scale * a[M,P].T @ b[M,Q]   (P <= 64)."""
+def wgrad_thin(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out[P,Q] (f32) = (out if accumulate else 0) + scale * a[M,P].T @ b[M,Q]   (P <= 64)."""
     _req(a, BF16, "wgrad_thin.a"); _req(b, BF16, "wgrad_thin.b"); _req(out, F32, "wgrad_thin.out")
     M, P = a.shape
     Q = b.shape[1]
     assert b.shape[0] == M and tuple(out.shape) == (P, Q)
     _l.check(_l.load().slam_wgrad_thin(a.data_ptr(), _row_major_2d(a, "wgrad.a"), P, b.data_ptr(), _row_major_2d(b, "wgrad.b"), Q, M,
-                                       scale, out.data_ptr(), _row_major_2d(out, "wgrad.out"), _stream()), "slam_wgrad_thin")
+                                       scale, out.data_ptr(), _row_major_2d(out, "wgrad.out"), 1 if accumulate else 0, _stream()), "slam_wgrad_thin")
     return out
 
 

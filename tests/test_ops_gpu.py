@@ -177,6 +177,9 @@ def test_wgrad_thin(ops):
     ops.wgrad_thin(a, b, out, scale=2.0)
     ref = 2.0 * a.float().t() @ b.float()
     assert rel_err(out, ref) < 1e-4
+    acc = out.clone()
+    ops.wgrad_thin(a, b, acc, scale=2.0, accumulate=True)              # accumulate mode: C += product
+    assert rel_err(acc, 2.0 * out) < 1e-5
     for (Mx, Px, Qx, ld) in ((1601, 8, 1024, 64), (333, 64, 6144, 64), (1600, 32, 520, 32), (70, 16, 4096, 16)):   # tensor-core path
         af = rnd(Mx, ld, seed=50)
         bx = rnd(Mx, Qx + 8, seed=51)[:, :Qx]
