@@ -273,27 +273,37 @@ __global__ void __launch_bounds__(128, (DH == 64 && MT == 1) ? 4 : 2) attn_fwd_k
 }
 
 // ------------------------------------------------------------------------------------------- backward
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]: dh / 8 lanes per (token, head) row with 16-byte loads, 32 / (dh / 8) rows per warp
 __global__ void attn_delta_kernel(const AttnP p, int dh) {
   pdl_trigger();
   pdl_wait();
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lpr = dh >> 3;                                   // lanes per row (dh = 64: 8, dh = 128: 16)
+  const int rpw = 32 / lpr;                                  // rows per warp
   const int lane = threadIdx.x & 31;
-  const int total = p.batch * p.sq * p.hq;
-  if (warp_global >= total) return;
-  const int h = warp_global % p.hq;
-  const long long tok = warp_global / p.hq;  // b * sq + i
-  const bf16* o = p.out + tok * p.ldo + h * dh;
-  const bf16* d = p.dout + tok * p.lddo + h * dh;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long total = static_cast<long long>(p.batch) * p.sq * p.hq;
+  const long long rowi = warp_global * rpw + lane / lpr;
+  const bool ok = rowi < total;
+  const long long rr = ok ? rowi : 0;
+  const int h = static_cast<int>(rr % p.hq);
+  const long long tok = rr / p.hq;                           // b * sq + i
+  const int c = (lane % lpr) * 8;
   float acc = 0.0f;
-  for (int c = lane * 2; c < dh; c += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + c));
-    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + c));
-    acc += a.x * g.x + a.y * g.y;
+  if (ok) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p.out + tok * p.ldo + h * dh + c);
+    const uint4 g = *reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + h * dh + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = unpack_bf16x2(aw[t]), y = unpack_bf16x2(gw[t]);
+      acc += x.x * y.x + x.y * y.y;
+    }
   }
-  acc = warp_sum(acc);
-  const int b = static_cast<int>(tok / p.sq), i = static_cast<int>(tok % p.sq);
-  if (lane == 0) p.delta[(static_cast<long long>(b) * p.hq + h) * p.sq + i] = acc;
+  for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (ok && (lane % lpr) == 0) {
+    const int bb = static_cast<int>(tok / p.sq), i = static_cast<int>(tok % p.sq);
+    p.delta[(static_cast<long long>(bb) * p.hq + h) * p.sq + i] = acc;
+  }
 }
 
 // One CTA = 64 keys of one (batch, kv head); loops over the q heads of the group and over query blocks.
@@ -657,7 +667,7 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
     set_error("attn_bwd: memset failed: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
   }
-  const int total_warps = p.batch * p.sq * p.hq;
+  const long long total_warps = ceil_div(static_cast<long long>(p.batch) * p.sq * p.hq, 32 / (a->dh / 8));
   launch_pdl(attn_delta_kernel, static_cast<unsigned>(ceil_div(total_warps, 8)), 256, 0, st, p, a->dh);
   SLAM_LAUNCH_CHECK("slam_attn_bwd.delta");
   static const bool use_tc = []() {

@@ -882,24 +882,39 @@ __global__ void dropout_bwd_add_kernel(const bf16* __restrict__ base, const bf16
 }
 
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW semantics, single tensor, fp32)
+__device__ __forceinline__ void adamw_elem(float& pv, float gi, float& mi, float& vi, float lr, float beta1, float beta2, float eps, float wd,
+                                           float bc1, float bc2_sqrt, float grad_div) {
+  const float grad = gi / grad_div;
+  pv *= (1.0f - lr * wd);
+  mi = beta1 * mi + (1.0f - beta1) * grad;
+  vi = beta2 * vi + (1.0f - beta2) * grad * grad;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pv -= (lr / bc1) * (mi / denom);
+}
+// 28 B of HBM traffic per parameter: 16-byte vectors (the arena buffers are 16-byte aligned), scalar tail
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                              float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_div) {
   pdl_trigger();
   pdl_wait();
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) {
-    const float grad = g[i] / grad_div;
-    float pv = p[i];
-    pv *= (1.0f - lr * wd);
-    const float mi = beta1 * m[i] + (1.0f - beta1) * grad;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * grad * grad;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pv -= (lr / bc1) * (mi / denom);
-    p[i] = pv;
+  for (; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_elem(pv.x, gv.x, mv.x, vv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_div);
+    adamw_elem(pv.y, gv.y, mv.y, vv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_div);
+    adamw_elem(pv.z, gv.z, mv.z, vv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_div);
+    adamw_elem(pv.w, gv.w, mv.w, vv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_div);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
   }
+  for (i = 4 * n4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    adamw_elem(p[i], g[i], m[i], v[i], lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_div);
 }
 
 }  // namespace slam
@@ -1104,7 +1119,7 @@ int slam_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_s
   if (n == 0) return 0;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step_host);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_host);
-  launch_pdl(adamw_kernel, ew_grid(n, 1, 256), 256, 0, ST(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+  launch_pdl(adamw_kernel, ew_grid(n, 4, 256), 256, 0, ST(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                            static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_div);
   SLAM_LAUNCH_CHECK("slam_adamw");
   return 0;
