@@ -33,6 +33,35 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+class _ZeroPool:
+    """fp32 scratch for the split-K thin products of one forward or backward pass: ONE memset per pass instead of one fill kernel per
+    product (64 of them per step); slices are handed out in call order and the pool grows to the largest pass seen."""
+
+    def __init__(self) -> None:
+        self.buf: Optional[torch.Tensor] = None
+        self.used = 0
+        self.need = 0
+
+    def begin(self, device) -> None:
+        if self.buf is None or self.buf.numel() < self.need:
+            self.buf = torch.empty(max(self.need, 1), device=device, dtype=F32)
+        self.buf.zero_()
+        self.used = 0
+
+    def take(self, m: int, n: int, device) -> torch.Tensor:
+        k = m * n
+        self.need = max(self.need, self.used + k)
+        if self.buf is None or self.used + k > self.buf.numel():
+            self.used += k
+            return torch.zeros((m, n), device=device, dtype=F32)           # first pass / larger batch: the pool is resized at the next begin()
+        out = self.buf[self.used: self.used + k].view(m, n)
+        self.used += k
+        return out
+
+
+_THIN_POOL = _ZeroPool()
+
+
 def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch.Tensor:
     """bf16 out = a @ b.T (+ a2 @ b2.T) for products with few output tiles but a long K (LoRA rank-64 products, lm_head dgrad):
     wide outputs (N >= 256) use the GEMM's own tail split (k-slices on idle SMs, deterministic exchange, bf16 epilogue);
@@ -47,7 +76,7 @@ def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch
     split = min(8, nkb // 4, max(1, 148 // tiles))
     if split <= 1:
         return ops.gemm(a, b, a2=a2, b2=b2)
-    return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out_f32=True, split_k=split))
+    return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out=_THIN_POOL.take(M, N, a.device), out_f32=True, split_k=split))
 
 
 def _require_cuda(device) -> torch.device:
@@ -486,6 +515,7 @@ class LlamaLoRAB200:
         H, Hkv, dh, Dq, Dkv = cfg.heads, cfg.kv_heads, cfg.dh, cfg.dq, cfg.dkv
         cos, sin = self.rope_tables(S)
         scale = 1.0 / math.sqrt(dh)
+        _THIN_POOL.begin(x.device)
         x = x.reshape(M, D)
         saved_layers = []
         for li, Lw in enumerate(self.layers):
@@ -525,6 +555,7 @@ class LlamaLoRAB200:
         H, Hkv, dh, Dq, Dkv = cfg.heads, cfg.kv_heads, cfg.dh, cfg.dq, cfg.dkv
         cos, sin = self.rope_tables(S)
         scale = 1.0 / math.sqrt(dh)
+        _THIN_POOL.begin(dxf.device)
         dx = ops.rmsnorm_bwd(dxf, sv["x_last"], self.norm, sv["rstd_f"])
         for li in range(cfg.layers - 1, -1, -1):
             Lw, kp = self.layers[li], sv["layers"][li]
