@@ -62,17 +62,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// MN-major, SWIZZLE_128B shared-memory matrix descriptor: rows of the tile run along K (8-row groups 1024 B apart = SBO),
-// 64 contiguous bf16 (128 B) along the MN dimension.
-__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;              // LBO: distance between 64-element MN blocks (single block per MMA here)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;      // SBO: distance between 8-row K groups
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
 // D=f32, A=bf16 K-major, B=bf16 with selectable major-ness
 __host__ __device__ constexpr uint32_t fa_idesc(uint32_t M, uint32_t N, uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
