@@ -16,7 +16,7 @@ import json
 import torch
 import whisper
 
-from . import _b200_common as common
+from slam_llm.datasets import _b200_common as common       # absolute: recipes load this file by PATH (dataset_config.file), outside the package
 
 
 class SpeechDatasetJsonl(torch.utils.data.Dataset):

@@ -23,7 +23,7 @@ import torch.distributed as dist
 import whisper
 from torch.utils.data import IterableDataset
 
-from . import _b200_common as common
+from slam_llm.datasets import _b200_common as common       # absolute: recipes load this file by PATH (dataset_config.file), outside the package
 
 _SPLIT_KEYS = {"train": "train_scp_file_path", "val": "dev_scp_file_path", "test": "test_scp_file_path"}
 

@@ -85,6 +85,17 @@ def test_plugin_loaders_follow_reference_error_behaviour(tmp_path):
         get_custom_model_factory(DictConfig({"file": f"{f}:missing"}), logging.getLogger())
 
 
+def test_dataset_files_load_as_path_plugins():
+    """Recipes address the datasets by FILE PATH (`dataset_config.file=.../speech_dataset.py:get_speech_dataset`, reference
+    utils/dataset_utils.py:14-57): the files must import cleanly when executed outside their package."""
+    from slam_llm.utils.dataset_utils import load_module_from_py_file, _plugin_factory
+    base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "src", "slam_llm", "datasets")
+    for name in ("speech_dataset.py", "speech_dataset_large.py"):
+        mod = load_module_from_py_file(os.path.join(base, name))
+        assert callable(mod.get_speech_dataset)
+        assert callable(_plugin_factory(os.path.join(base, name) + ":get_speech_dataset"))
+
+
 def test_generate_peft_config():
     from slam_llm.utils.config_utils import generate_peft_config
     tc = DictConfig({"peft_config": {"peft_method": "lora", "r": 16, "lora_alpha": 32, "target_modules": ["q_proj", "v_proj"], "bias": "none",
