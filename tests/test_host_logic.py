@@ -96,6 +96,22 @@ def test_dataset_files_load_as_path_plugins():
         assert callable(_plugin_factory(os.path.join(base, name) + ":get_speech_dataset"))
 
 
+def test_zero_pool_hands_out_zeroed_disjoint_slices():
+    """Scratch for the split-K thin products (engine._ZeroPool): one memset per pass, slices in call order, grows to the largest pass."""
+    from slam_llm_b200.engine import _ZeroPool
+    pool = _ZeroPool()
+    pool.begin("cpu")
+    first = pool.take(4, 8, "cpu")                      # nothing reserved yet: falls back to a fresh zero tensor and records the need
+    assert first.shape == (4, 8) and float(first.abs().sum()) == 0.0
+    first.fill_(1.0)
+    for _ in range(2):
+        pool.begin("cpu")
+        a, b = pool.take(4, 8, "cpu"), pool.take(2, 8, "cpu")
+        assert float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0 and a.data_ptr() != b.data_ptr()
+        a.fill_(2.0); b.fill_(3.0)                      # dirty them: the next begin() must clear the pool again
+    assert pool.buf.numel() >= 48 and a.data_ptr() == pool.buf.data_ptr()
+
+
 def test_generate_peft_config():
     from slam_llm.utils.config_utils import generate_peft_config
     tc = DictConfig({"peft_config": {"peft_method": "lora", "r": 16, "lora_alpha": 32, "target_modules": ["q_proj", "v_proj"], "bias": "none",
