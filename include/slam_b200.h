@@ -118,7 +118,9 @@ int slam_layernorm(const void* x_bf16, const float* w, const float* b, void* y_b
  *   q [B,Sq,Hq,dh], k/v [B,Sk,Hkv,dh] given as base pointers + row strides (elements) so that the
  *   fused QKV buffer can be used in place.  causal: 0/1.  key_mask u8 [B,Sk] (1 = attend) or NULL.
  *   lse f32 [B,Hq,Sq] (log-sum-exp, natural log) or NULL.  out bf16 [B,Sq,Hq,dh] with row stride ldo.
- * Replaces whisper MultiHeadAttention.qkv_attention and HF LlamaAttention (eager softmax). */
+ * Replaces whisper MultiHeadAttention.qkv_attention and HF LlamaAttention (eager softmax).
+ * Kernels: tcgen05 / TMEM flash attention for dh = 64 / 128 with Sq == Sk >= 64 (forward) and dh = 128 (backward);
+ * mma.sync flash kernels for every other shape - same arguments, same results within bf16 rounding. */
 typedef struct slam_attn_args {
   const void* q; int64_t ldq;   /* row stride between consecutive tokens, elements */
   const void* k; int64_t ldk;
