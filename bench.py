@@ -216,6 +216,32 @@ def cpu_reference(wl, steps, warmup, budget_s=150.0, quiet=True):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# B-EAGER: the reference's eager HF/PEFT step on the same GPU, same batch (baseline/eager_hf.py); N=1 only
+# ----------------------------------------------------------------------------------------------------------------------
+def eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, our_e2e, steps=20, warmup=5):
+    """Frees this repo's engine state, builds HF WhisperEncoder + LlamaForCausalLM (fp32 master weights) with restated peft LoRA, and times the
+    reference train-loop body (fp16 autocast + GradScaler + AdamW, train_utils.py:112-149) on the same synthetic batch; the log-mel the
+    reference computes in its DataLoader workers is prepared outside the timed region (generous to the baseline)."""
+    try:
+        from baseline import eager_hf
+        mel = eng.log_mel(host_batch["audio_pcm"].to(dev)).float().cpu()
+        for k in list(vars(eng)):
+            setattr(eng, k, None)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        r = eager_hf.run(enc, llm, lora, host_batch, mel, steps=steps, warmup=warmup, device=dev)
+        value = audio_s / (r["ms_per_step"] / 1e3)
+        return {"value": round(value, 2), "unit": UNIT, "ms_per_step": round(r["ms_per_step"], 2), "wall_ms_per_step": round(r["wall_ms_per_step"], 2),
+                "steps": steps, "warmup": warmup, "dtype": "fp16 autocast over fp32 master weights + GradScaler", "same_config": True,
+                "path": "HF WhisperEncoder modules (sdpa) + HF LlamaForCausalLM (eager attention) + restated peft-0.6 LoRA + torch.optim.AdamW; "
+                        "batch incl. CPU-side log-mel resident on the device", "peak_mem_gb": r["peak_mem_gb"],
+                "speedup_e2e": round(our_e2e / value, 2), "last": r["last"]}
+    except Exception as e:  # the baseline leg must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -342,6 +368,9 @@ def run_ours(args):
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    eager = None
+    if world == 1 and not args.skip_eager:
+        eager = eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, e2e_value)
     cb = None
     if world == 1 and not args.skip_cpu:
         cb, _ = cpu_reference(wl, steps=2, warmup=0, budget_s=25.0)
@@ -354,7 +383,7 @@ def run_ours(args):
                        "lm_head_rows": "rows with a label only (loss/grad identical to full logits; eval path computes all rows)"},
             "clocks": clocks, "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                                       "ms_per_step": round(ms2 / args.steps, 3)},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "loss": round(final_loss, 4)}
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "eager_gpu_baseline": eager, "loss": round(final_loss, 4)}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -368,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-eager", action="store_true", help="skip the eager-HF-on-GPU baseline leg (B-EAGER)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -79,26 +79,53 @@ def setup_encoder(train_config, model_config, **kwargs):
 # ---------------------------------------------------------------------------------------------------------------------
 # LLM module: HF LlamaForCausalLM + peft LoRA surface over LlamaLoRAB200
 # ---------------------------------------------------------------------------------------------------------------------
+def random_init_allowed(model_config=None) -> bool:
+    """Frozen weights are drawn at random ONLY on explicit request (benchmarks / offline tests): `model_config.b200_random_init=true` or
+    SLAM_B200_RANDOM_INIT=1.  Otherwise a missing checkpoint is an error, like from_pretrained / whisper.load_model in the reference."""
+    if os.environ.get("SLAM_B200_RANDOM_INIT", "0") == "1":
+        return True
+    return bool(model_config.get("b200_random_init", False)) if model_config is not None else False
+
+
 def _load_llm_cfg(llm_path: str) -> LlmCfg:
     with open(os.path.join(llm_path, "config.json")) as f:
         c = json.load(f)
     if c.get("model_type", "llama") not in ("llama", "mistral"):
         raise NotImplementedError(f"model_type={c.get('model_type')!r}: the B200 decoder implements the Llama architecture")
-    return LlmCfg(vocab=c["vocab_size"], d=c["hidden_size"], layers=c["num_hidden_layers"], heads=c["num_attention_heads"],
-                  kv_heads=c.get("num_key_value_heads", c["num_attention_heads"]), ffn=c["intermediate_size"],
+    heads, hidden = c["num_attention_heads"], c["hidden_size"]
+    # fields that change the arithmetic and are NOT implemented by the kernels: refuse instead of computing something else silently
+    if c.get("rope_scaling") not in (None, {}):
+        raise NotImplementedError(f"rope_scaling={c['rope_scaling']!r} (Llama-3.1/3.2 style scaled RoPE) is not implemented by the B200 decoder")
+    if c.get("head_dim") not in (None, hidden // heads):
+        raise NotImplementedError(f"head_dim={c['head_dim']} != hidden_size/num_attention_heads={hidden // heads}")
+    if c.get("attention_bias", False) or c.get("mlp_bias", False):
+        raise NotImplementedError("attention_bias / mlp_bias checkpoints are not implemented by the B200 decoder (Llama linears have no bias)")
+    if c.get("hidden_act", "silu") != "silu":
+        raise NotImplementedError(f"hidden_act={c['hidden_act']!r}: the fused MLP implements SwiGLU (silu)")
+    if c.get("sliding_window") not in (None, 0) and c.get("model_type") == "mistral":
+        raise NotImplementedError(f"sliding_window={c['sliding_window']}: the B200 attention kernels are full causal")
+    return LlmCfg(vocab=c["vocab_size"], d=hidden, layers=c["num_hidden_layers"], heads=heads,
+                  kv_heads=c.get("num_key_value_heads", heads), ffn=c["intermediate_size"],
                   rope_theta=float(c.get("rope_theta", 10000.0)), eps=float(c.get("rms_norm_eps", 1e-5)))
 
 
 def _load_llm_weights(llm_path: str) -> Optional[Dict[str, torch.Tensor]]:
-    files = sorted(f for f in os.listdir(llm_path) if f.endswith(".safetensors"))
-    if not files:
-        return None
-    from safetensors.torch import load_file
+    """HF checkpoint directory -> {name: tensor}: *.safetensors shards, else pytorch_model*.bin shards.  None when the directory holds no weights."""
+    names = sorted(os.listdir(llm_path))
     out: Dict[str, torch.Tensor] = {}
-    for f in files:
-        out.update(load_file(os.path.join(llm_path, f)))
+    st = [f for f in names if f.endswith(".safetensors")]
+    if st:
+        from safetensors.torch import load_file
+        for f in st:
+            out.update(load_file(os.path.join(llm_path, f)))
+    else:
+        bins = [f for f in names if f.startswith("pytorch_model") and f.endswith(".bin")]
+        for f in bins:
+            out.update(torch.load(os.path.join(llm_path, f), map_location="cpu", weights_only=True))
+    if not out:
+        return None
     if "lm_head.weight" not in out:
-        out["lm_head.weight"] = out["model.embed_tokens.weight"]
+        out["lm_head.weight"] = out["model.embed_tokens.weight"]                 # tie_word_embeddings
     return out
 
 
@@ -131,9 +158,10 @@ class LlamaB200ForCausalLM(nn.Module):
     """Frozen Llama decoder (+ optional LoRA adapters under peft-0.6 key names).  Weights are materialised when the
     module is bound to a step arena by slam_model.__init__."""
 
-    def __init__(self, cfg: LlmCfg, llm_path: str, lora_cfg, use_peft: bool):
+    def __init__(self, cfg: LlmCfg, llm_path: str, lora_cfg, use_peft: bool, allow_random_init: bool = False, peft_ckpt: Optional[str] = None):
         super().__init__()
         self.cfg, self.llm_path, self.lora_cfg, self.use_peft = cfg, llm_path, lora_cfg if use_peft else None, use_peft
+        self.allow_random_init, self.peft_ckpt = allow_random_init, peft_ckpt
         self.b200: Optional[LlamaLoRAB200] = None
         object.__setattr__(self, "_step", None)
         D, Dkv, F, V, L = cfg.d, cfg.dkv, cfg.ffn, cfg.vocab, cfg.layers
@@ -150,11 +178,14 @@ class LlamaB200ForCausalLM(nn.Module):
                     return mods["base_model"]._modules["model"]
             raise
 
-    def bind(self, arena: TrainableArena, device) -> None:
+    def bind(self, arena: TrainableArena, device, seed: int = 42) -> None:
         weights = _load_llm_weights(self.llm_path)
         if weights is None:
-            logger.warning(f"no *.safetensors under {self.llm_path}: RANDOM-INIT {self.cfg} (offline / benchmark mode)")
-        self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights)
+            if not self.allow_random_init:
+                raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under llm_path={self.llm_path!r} (set model_config.b200_random_init=true "
+                                        "or SLAM_B200_RANDOM_INIT=1 to benchmark with random frozen weights)")
+            logger.warning(f"no weights under {self.llm_path}: RANDOM-INIT {self.cfg} (b200_random_init)")
+        self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights, seed=seed + 1)
 
     def register_views(self, arena: TrainableArena) -> None:
         """Expose the embedding module and the LoRA adapters under the reference / peft key names."""
@@ -191,16 +222,49 @@ def setup_llm(train_config, model_config, **kwargs):
         raise NotImplementedError("8-bit quantised loading is out of scope of the B200 path")
     if not train_config.freeze_llm:
         raise NotImplementedError("freeze_llm=false (full fine-tune) needs wgrad for every linear: SURVEY.md §8f rank 3, not built yet")
-    if kwargs.get("peft_ckpt", None):
-        raise NotImplementedError("peft_ckpt directories: pass the trainable-only model.pt via ckpt_path instead")
     cfg = _load_llm_cfg(model_config.llm_path)
-    lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
-    model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, bool(train_config.use_peft))
+    peft_ckpt = kwargs.get("peft_ckpt", None)
+    if peft_ckpt:                                                    # slam_model.py:210-213: PeftModel.from_pretrained(model, peft_ckpt, is_trainable=True)
+        logger.info("loading peft_ckpt from: {}".format(peft_ckpt))
+        lora_cfg = _peft_dir_config(peft_ckpt)
+    else:
+        lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
+    use_peft = bool(peft_ckpt) or bool(train_config.use_peft)
+    model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, use_peft, allow_random_init=random_init_allowed(model_config),
+                                 peft_ckpt=peft_ckpt or None)
     print_module_size(model, model_config.llm_name, _rank(train_config))
     model.eval()
-    if train_config.use_peft:
+    if train_config.use_peft and not peft_ckpt:
         logger.info("setup peft...")
     return model
+
+
+def _peft_dir_config(peft_dir: str):
+    """adapter_config.json of a peft checkpoint directory -> the LoRA config the engine needs (r, alpha, targets, dropout)."""
+    from slam_llm_b200.config import LoraCfg
+    with open(os.path.join(peft_dir, "adapter_config.json")) as f:
+        c = json.load(f)
+    if c.get("peft_type", "LORA") != "LORA":
+        raise NotImplementedError(f"peft_type={c.get('peft_type')!r}: only LoRA adapters are implemented")
+    if c.get("bias", "none") != "none" or c.get("modules_to_save"):
+        raise NotImplementedError("peft checkpoints with trainable biases / modules_to_save are not implemented")
+    return LoraCfg(int(c["r"]), int(c["lora_alpha"]), tuple(c["target_modules"]), float(c.get("lora_dropout", 0.0)))
+
+
+def _peft_dir_state(peft_dir: str) -> Dict[str, torch.Tensor]:
+    """adapter_model.{safetensors,bin} -> reference state-dict names: peft saves `...q_proj.lora_A.weight` (adapter name stripped);
+    the live module calls it `...q_proj.lora_A.default.weight`, under the `llm.` attribute of slam_model."""
+    st = os.path.join(peft_dir, "adapter_model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        sd = load_file(st)
+    else:
+        sd = torch.load(os.path.join(peft_dir, "adapter_model.bin"), map_location="cpu", weights_only=True)
+    out = {}
+    for k, v in sd.items():
+        k = k.replace(".lora_A.weight", ".lora_A.default.weight").replace(".lora_B.weight", ".lora_B.default.weight")
+        out["llm." + k] = v
+    return out
 
 
 def setup_encoder_projector(train_config, model_config, **kwargs):
@@ -259,11 +323,20 @@ class slam_model(nn.Module):
         arena = TrainableArena()
         proj_cfg = ProjCfg(encoder_projector.kind, encoder_projector.k, encoder_projector.linear1.out_features)
         eng_proj = ProjectorB200(encoder.b200.cfg, llm.cfg, proj_cfg, arena)
-        llm.bind(arena, device)
+        seed = int(train_config.get("seed", 42))                    # adapters + LoRA dropout follow train_config.seed like the reference's global RNG
+        llm.bind(arena, device, seed=seed)
         arena.finalize(device)
         encoder_projector.bind(eng_proj, arena)
-        llm.b200.init_lora(None)                                    # peft init: A kaiming-uniform, B zeros
+        llm.b200.init_lora(None, seed=seed + 2)                     # peft init: A kaiming-uniform, B zeros
         llm.register_views(arena)
+        if llm.peft_ckpt:
+            sd = _peft_dir_state(llm.peft_ckpt)
+            mine = llm.b200.lora_state()
+            unknown = sorted(set(sd) - set(mine))
+            if unknown:
+                raise KeyError(f"peft_ckpt holds adapters this model does not have: {unknown[:4]} ...")
+            for k, v in sd.items():
+                mine[k].copy_(v.to(device, torch.float32))
         self.b200 = SlamStepB200.from_parts(encoder.b200, eng_proj, llm.b200, arena, device)
         object.__setattr__(llm, "_step", self)       # plain attribute: registering the parent as a sub-module would create a cycle
         arena.param.requires_grad_(True)

@@ -56,7 +56,7 @@ def run_config(llm_dir, jsonl, out_dir, model_file, dataset_file, **train_over):
                             fix_length_audio=-1, inference_mode=False, input_type="mel", mel_size=80, normalize=False),
         model_config=dict(file=model_file, llm_name="tiny-llama-test", llm_path=llm_dir, llm_type="decoder_only", llm_dim=256, encoder_name="whisper",
                           encoder_ds_rate=2, encoder_path="tiny", encoder_dim=384, encoder_projector="linear", encoder_projector_ds_rate=5,
-                          modal="audio", normalize=False, encoder_type="finetune"),
+                          modal="audio", normalize=False, encoder_type="finetune", b200_random_init=True),
         train_config=train,
         log_config=dict(use_wandb=False, wandb_dir=out_dir, wandb_entity_name="x", wandb_project_name="x", wandb_exp_name="x",
                         log_file=os.path.join(out_dir, "train.log"), log_interval=5),

@@ -1,0 +1,132 @@
+"""Checkpoint files -> recipe surface -> the reference run's numbers (SURVEY §8 f2 + b).
+
+Fabricated files in the formats the reference loads — an HF safetensors Llama directory (llm_path), an openai-whisper .pt
+(encoder_path: dims + model_state_dict) or an HF Whisper directory (encoder_path_hf), a trainable-only model.pt (ckpt_path,
+checkpoint_handler.py:185-201 key names) or a peft adapter directory (peft_ckpt) — hold exactly the weights of the committed
+reference-run fixture tests/golden/ref_tiny.pt.  `model_factory` must then reproduce the reference's loss and gradients through
+`model(**batch)` / `outputs.loss.backward()` (the calls utils/train_utils.py:113,130 make)."""
+import json
+import os
+
+import pytest
+import torch
+
+import ref_fixture as rf
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_assets(tmp, fix, om, hf_whisper: bool, peft_dir: bool):
+    from safetensors.torch import save_file
+    from recipe_util import make_llm_dir
+    enc, llm, lora, proj = rf.cfgs(fix)
+    llm_dir = make_llm_dir(os.path.join(tmp, "llm"), vocab=llm.vocab, hidden=llm.d, layers=llm.layers, heads=llm.heads, kv_heads=llm.kv_heads, ffn=llm.ffn)
+    save_file({k: v.contiguous() for k, v in om.llm_w.items()}, os.path.join(llm_dir, "model.safetensors"))
+    mc = dict(llm_name="tiny-llama", llm_path=llm_dir, llm_dim=llm.d, encoder_name="whisper", encoder_dim=enc.d, encoder_projector=proj.kind,
+              encoder_projector_ds_rate=proj.k, encoder_path=None)
+    if hf_whisper:
+        names = {"attn.query": "self_attn.q_proj", "attn.key": "self_attn.k_proj", "attn.value": "self_attn.v_proj", "attn.out": "self_attn.out_proj",
+                 "attn_ln": "self_attn_layer_norm", "mlp.0": "fc1", "mlp.2": "fc2", "mlp_ln": "final_layer_norm"}
+        w = om.enc_w
+        sd = {"model.encoder.embed_positions.weight": w["positional_embedding"], "model.encoder.layer_norm.weight": w["ln_post.weight"],
+              "model.encoder.layer_norm.bias": w["ln_post.bias"]}
+        for c in ("conv1", "conv2"):
+            sd[f"model.encoder.{c}.weight"], sd[f"model.encoder.{c}.bias"] = w[f"{c}.weight"], w[f"{c}.bias"]
+        for i in range(enc.layers):
+            for o, h in names.items():
+                for sfx in ("weight", "bias"):
+                    if f"blocks.{i}.{o}.{sfx}" in w:
+                        sd[f"model.encoder.layers.{i}.{h}.{sfx}"] = w[f"blocks.{i}.{o}.{sfx}"]
+        wdir = os.path.join(tmp, "whisper_hf")
+        os.makedirs(wdir)
+        json.dump(dict(model_type="whisper", num_mel_bins=enc.n_mels, max_source_positions=enc.n_ctx, d_model=enc.d, encoder_attention_heads=enc.heads,
+                       encoder_layers=enc.layers), open(os.path.join(wdir, "config.json"), "w"))
+        save_file({k: v.contiguous() for k, v in sd.items()}, os.path.join(wdir, "model.safetensors"))
+        mc["encoder_path_hf"] = wdir
+    else:
+        wpt = os.path.join(tmp, "whisper_enc.pt")
+        dims = dict(n_mels=enc.n_mels, n_audio_ctx=enc.n_ctx, n_audio_state=enc.d, n_audio_head=enc.heads, n_audio_layer=enc.layers, n_vocab=8, n_text_ctx=8,
+                    n_text_state=enc.d, n_text_head=enc.heads, n_text_layer=0)
+        torch.save({"dims": dims, "model_state_dict": {"encoder." + k: v for k, v in om.enc_w.items()}}, wpt)
+        mc["encoder_path"] = wpt
+    kwargs = {}
+    trainable = {k: v.detach().clone() for k, v in om.trainable().items()}
+    if peft_dir:
+        pdir = os.path.join(tmp, "peft")
+        os.makedirs(pdir)
+        json.dump(dict(peft_type="LORA", r=lora.r, lora_alpha=lora.alpha, target_modules=list(lora.targets), lora_dropout=0.0, bias="none", task_type="CAUSAL_LM"),
+                  open(os.path.join(pdir, "adapter_config.json"), "w"))
+        torch.save({k[len("llm."):].replace(".default.weight", ".weight"): v for k, v in trainable.items() if k.startswith("llm.")},
+                   os.path.join(pdir, "adapter_model.bin"))
+        kwargs["peft_ckpt"] = pdir
+        trainable = {k: v for k, v in trainable.items() if not k.startswith("llm.")}
+    ckpt = os.path.join(tmp, "model.pt")
+    torch.save(trainable, ckpt)
+    kwargs["ckpt_path"] = ckpt
+    return mc, kwargs
+
+
+@pytest.mark.parametrize("hf_whisper,peft_dir", [(False, False), (True, True)])
+def test_model_factory_from_checkpoint_files_reproduces_the_reference_run(tmp_path, hf_whisper, peft_dir):
+    import slam_llm  # noqa: F401
+    from omegaconf import OmegaConf
+    from slam_llm.models.slam_model import model_factory
+    fix = rf.load("ref_tiny.pt")
+    om = rf.oracle_model(fix)
+    enc, llm, lora, proj = rf.cfgs(fix)
+    mc, kwargs = _write_assets(str(tmp_path), fix, om, hf_whisper, peft_dir)
+    # with a peft directory the adapter shape comes from adapter_config.json, not from train_config.peft_config (slam_model.py:210-213)
+    tc = dict(enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=not peft_dir, seed=42,
+              peft_config=dict(peft_method="lora", r=lora.r, lora_alpha=lora.alpha, target_modules=list(lora.targets), bias="none", task_type="CAUSAL_LM",
+                               lora_dropout=0.0, inference_mode=False))
+    model, tok = model_factory(OmegaConf.create(tc), OmegaConf.create(mc), metric="acc", **kwargs)
+    model.train()
+    # the engine holds exactly the file contents
+    w = model.b200.llm.layers[1]["wo"].float().cpu()
+    assert torch.equal(w, om.llm_w["model.layers.1.self_attn.o_proj.weight"].bfloat16().float())
+    st = model.b200.trainable_state()
+    for k, v in om.trainable().items():
+        assert torch.equal(st[k].cpu(), v.detach()), k
+    batch = rf.batch_of(fix)
+    outputs, acc = model(**{k: v.cuda() for k, v in batch.items()})
+    assert abs(outputs.loss.item() - fix["loss"]) <= 5e-3 * abs(fix["loss"]), (outputs.loss.item(), fix["loss"])
+    outputs.loss.backward()
+    named = dict(model.named_parameters())
+    gmax = max((g["norm"] if rf.is_probe(g) else g.norm().item()) for g in fix["grads"].values())
+    checked = 0
+    for k, g_ref in fix["grads"].items():
+        g = named[k].grad
+        assert g is not None, k
+        if rf.is_probe(g_ref):
+            if g_ref["norm"] >= 1e-3 * gmax:
+                rf.check_probe(g, g_ref, norm_rel=3e-2, head_cos=0.99, what=k)
+                checked += 1
+        elif g_ref.norm().item() >= 1e-3 * gmax:
+            assert rf.cosine(g, g_ref) > 0.99 and rf.rel_l2(g, g_ref) < 3e-2, (k, rf.cosine(g, g_ref), rf.rel_l2(g, g_ref))
+            checked += 1
+    assert checked >= 6
+    # eval forward returns real logits for every position (evaluation() decodes argmax(logits), train_utils.py:410-446)
+    model.eval()
+    with torch.no_grad():
+        out_eval, _ = model(**{k: v.cuda() for k, v in batch.items()})
+    rows = rf.label_rows(batch["labels"])
+    lab = out_eval.logits.float().cpu()[:, :-1][rows]
+    assert rf.rel_max(lab, fix["label_logits"]) < 2e-2 and rf.cosine(lab, fix["label_logits"]) > 0.999
+    if hf_whisper:                                                          # recipes call `self.encoder(mel).last_hidden_state` on HF encoders
+        mel = model.b200.log_mel(batch["audio_pcm"].cuda())
+        h = model.encoder(mel.permute(0, 2, 1)).last_hidden_state
+        assert rf.rel_max(h[:, :40], fix["encoder_out"]) < 2e-2
+
+
+def test_missing_llm_weights_fail_loudly_on_the_gpu_box(tmp_path, monkeypatch):
+    import slam_llm  # noqa: F401
+    from omegaconf import OmegaConf
+    from recipe_util import make_llm_dir
+    from slam_llm.models.slam_model import model_factory
+    monkeypatch.delenv("SLAM_B200_RANDOM_INIT", raising=False)
+    llm_dir = make_llm_dir(str(tmp_path / "llm"))
+    tc = OmegaConf.create(dict(enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=False, seed=42))
+    mc = OmegaConf.create(dict(llm_name="x", llm_path=llm_dir, llm_dim=256, encoder_name="whisper", encoder_path="tiny", encoder_dim=384,
+                               encoder_projector="linear", encoder_projector_ds_rate=5))
+    with pytest.raises(FileNotFoundError):
+        model_factory(tc, mc)
