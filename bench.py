@@ -242,6 +242,66 @@ def eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, our_e2e, s
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# N>1 diagnostic: where does the weak-scaling loss come from?
+# ----------------------------------------------------------------------------------------------------------------------
+def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
+    """Per-rank device time of `steps` steps in three modes: (a) independent replicas (no collective: pure per-GPU speed under the shared
+    power/thermal envelope), (b) blocking all-reduce after backward (round-1 design), (c) async all-reduce + deferred AdamW.  Also the host
+    enqueue time per step and, for (b), the device time spent inside the all-reduce (which includes waiting for the slowest rank)."""
+    import torch.distributed as dist
+
+    def run(mode):
+        eng.flush_update()
+        eng.defer_update = mode == "overlap"
+        ar_events = []
+        for it in range(3 + steps):
+            if it == 3:
+                dist.barrier()
+                torch.cuda.synchronize()
+                t_host = time.perf_counter()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            loss, acc, _ = eng.forward(dev_batch, train=True)
+            eng.backward()
+            if mode == "blocking":
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                eng.allreduce_grads(async_op=False)
+                a1.record()
+                if it >= 3:
+                    ar_events.append((a0, a1))
+            elif mode == "overlap":
+                eng.allreduce_grads(async_op=True)
+            eng.optimizer_step(lr, 0.0, grad_div=float(world) if mode != "independent" else 1.0)
+        eng.flush_update()
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        host_ms = (time.perf_counter() - t_host) * 1e3 / steps
+        torch.cuda.synchronize()
+        out = {"ms_per_step": e0.elapsed_time(e1) / steps, "host_enqueue_ms_per_step": host_ms}
+        if ar_events:
+            out["allreduce_ms_per_step"] = sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events)
+        return out
+
+    res = {m: run(m) for m in ("independent", "blocking", "overlap")}
+    try:
+        smi = subprocess.run(["nvidia-smi", f"--id={dev.index}", "--query-gpu=clocks.sm,power.draw,temperature.gpu", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+    except Exception:
+        smi = ""
+    res["smi_after"] = smi
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        summary = {m: {"max_ms": max(g[m]["ms_per_step"] for g in gathered), "min_ms": min(g[m]["ms_per_step"] for g in gathered)} for m in ("independent", "blocking", "overlap")}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"scale_breakdown_n{world}.json"), "w") as f:
+            json.dump({"world": world, "steps": steps, "summary": summary, "ranks": gathered}, f, indent=1)
+        print("[breakdown] " + json.dumps(summary), file=sys.stderr, flush=True)
+    eng.defer_update = world > 1 and args.overlap == 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -272,6 +332,7 @@ def run_ours(args):
     enc, llm = C.WHISPER[wl["enc"]], C.LLM[wl["llm"]]
     lora, proj = C.LoraCfg(wl["r"], wl["alpha"], tuple(wl["targets"])), C.ProjCfg("linear", 5, 2048)
     eng = SlamStepB200(enc, llm, lora, proj, device=dev, seed=42, lora_b_std=0.02)
+    eng.defer_update = world > 1 and args.overlap == 1      # async gradient all-reduce, update applied behind the next step's frozen front end
     host_batch, S = make_batch(wl, llm.vocab, seed=42 + rank, pin=True)
     rows, tgts = SlamStepB200.label_rows(host_batch["labels"])
     host_batch["_rows"], host_batch["_targets"] = rows.pin_memory(), tgts.pin_memory()
@@ -305,6 +366,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         loss, acc = step_resident()
+    eng.flush_update()                                                # deferred mode: the K-th update lands inside the timed region
     e1.record()
     barrier()
     launches = ops.launch_count() - l0
@@ -341,6 +403,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         step_e2e()
+    eng.flush_update()
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1)
@@ -351,7 +414,11 @@ def run_ours(args):
     e2e_value = world * audio_s / (ms2 / args.steps / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
 
+    if args.breakdown:
+        scale_breakdown(args, eng, dev_batch, lr, rank, world, dev)
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     peak_tf, peak_hbm, peak_src = measured_peaks()
     fl = C.step_flops(enc, llm, proj, lora, B, wl["seconds"] * 100, S, n_label_rows=rows.numel())
@@ -379,6 +446,8 @@ def run_ours(args):
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                       "grad_allreduce": ("none" if world == 1 else "async NCCL all-reduce of the flat fp32 arena, AdamW deferred behind the next step's frozen front end"
+                                          if eng.defer_update else "blocking NCCL all-reduce of the flat fp32 arena"),
                        "l2": "per-step working set (35 GB bf16 weights streamed from HBM) >> 126 MB L2; no flush needed",
                        "lm_head_rows": "rows with a label only (loss/grad identical to full logits; eval path computes all rows)"},
             "clocks": clocks, "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -397,6 +466,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--overlap", type=int, default=1, help="N>1: 1 = async all-reduce + deferred AdamW (default), 0 = blocking all-reduce")
+    ap.add_argument("--breakdown", action="store_true", help="N>1 diagnostic: per-rank step time without / with blocking / with overlapped all-reduce "
+                                                              "-> gpurun_out/scale_breakdown_n{N}.json")
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-HF-on-GPU baseline leg (B-EAGER)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -617,9 +617,17 @@ class SlamStepB200:
         self._ctx = None
         self.micro_steps = 0   # backward() calls since the last optimizer step (gradient accumulation)
         self.lora_dropout_enabled = True   # module.train()/eval() of the host mirror toggles this (reference quirk Q6)
+        # Deferred update (data-parallel overlap): optimizer_step() only RECORDS the update; it is applied by flush_update(), which the next
+        # forward() calls AFTER launching the frozen front end (log-mel + Whisper encoder, independent of the trainables).  The gradient
+        # all-reduce issued with async_op=True therefore overlaps ~a quarter of the next step, and a rank that arrives early at the
+        # collective keeps computing instead of idling (per-step jitter between power-capped GPUs is absorbed).
+        self.defer_update = False
+        self._pending_update = None        # (lr, weight_decay, grad_div)
+        self._pending_work = None          # torch.distributed Work of the in-flight gradient all-reduce
 
     # ------------------------------------------------------------------ state dict in the reference's key names
     def trainable_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
+        self.flush_update()
         out = {n: self.arena.view(n, which) for n in self.arena.names() if n.startswith(ProjectorB200.PREFIX)}
         out.update(self.llm.lora_state(which))
         return out
@@ -670,10 +678,11 @@ class SlamStepB200:
         else:
             mel = mel.to(dev, F32)
         B, S = ids.shape
+        enc_out = self.encoder.forward(mel)                                                # frozen: does not read the trainables
+        self.flush_update()                                                                # (deferred mode) all-reduce wait + AdamW of the previous step
         self.llm.pack_lora()                                                               # adapters change every optimizer step
         self.llm.dropout_active = bool(train and self.lora_dropout_enabled and self.llm.dropout_p > 0.0)
         self.llm.dropout_step += 1
-        enc_out = self.encoder.forward(mel)
         aud = self.projector.forward(enc_out, save=train)
         x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
         xf = self.llm.forward(x, key_mask, save=train)
@@ -701,6 +710,7 @@ class SlamStepB200:
         c = self._ctx
         self._ctx = None
         dev = self.device
+        self.flush_update()                                                               # never overwrite gradients an update still needs
         carry = self.arena.grad.clone() if self.micro_steps > 0 else None                 # gradient accumulation: kernels overwrite
         self.arena.grad.zero_()                                                           # one memset: the LoRA wgrad products accumulate
         gs = (1.0 / c["nv"]) if grad_out is None else (grad_out.to(dev, F32).reshape(1) / c["nv"])
@@ -724,14 +734,35 @@ class SlamStepB200:
             self.arena.grad.add_(carry)
         self.micro_steps += 1
 
-    def optimizer_step(self, lr: float, weight_decay: float = 0.0, grad_div: float = 1.0) -> None:
-        self.arena.adamw_step(lr, weight_decay, grad_div=grad_div)
+    def allreduce_grads(self, async_op: bool = False):
+        """The one data-path collective (DDP's bucket all-reduce, pipeline/finetune.py:181-184): SUM over ranks of the flat
+        gradient arena (AdamW divides by the world size).  async_op: NCCL runs it on its own stream behind the kernels already queued;
+        the Work is kept and waited for (stream-side, no host block) by flush_update()."""
+        if async_op:
+            self._pending_work = torch.distributed.all_reduce(self.arena.grad, async_op=True)
+        else:
+            torch.distributed.all_reduce(self.arena.grad)
+
+    def optimizer_step(self, lr: float, weight_decay: float = 0.0, grad_div: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        self._pending_update = (lr, weight_decay, grad_div, betas, eps)
         self.micro_steps = 0
+        if not self.defer_update:
+            self.flush_update()
+
+    def flush_update(self) -> None:
+        """Apply the recorded optimizer step (no-op when none is pending).  Everything that reads the trainables calls this first."""
+        if self._pending_work is not None:
+            self._pending_work.wait()                                                      # current stream waits for the NCCL stream
+            self._pending_work = None
+        if self._pending_update is not None:
+            lr, weight_decay, grad_div, betas, eps = self._pending_update
+            self._pending_update = None
+            self.arena.adamw_step(lr, weight_decay, betas=betas, eps=eps, grad_div=grad_div)
 
     def train_step(self, batch, lr: float = 1e-4, weight_decay: float = 0.0, world_size: int = 1):
         loss, acc, _ = self.forward(batch, train=True)
         self.backward()
         if world_size > 1:
-            torch.distributed.all_reduce(self.arena.grad)                                   # the one data-path collective
+            self.allreduce_grads(async_op=self.defer_update)
         self.optimizer_step(lr, weight_decay, grad_div=float(world_size))
         return loss, acc

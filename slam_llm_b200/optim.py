@@ -19,8 +19,8 @@ class FlatAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         g = self.param_groups[0]
         world = getattr(self.model, "ddp_world_size", 1)
-        self.engine.arena.adamw_step(g["lr"], g["weight_decay"], betas=g["betas"], eps=g["eps"], grad_div=float(world))
-        self.engine.micro_steps = 0
+        # recorded now, applied by the engine (immediately, or - deferred data-parallel mode - after the next step's frozen front end)
+        self.engine.optimizer_step(g["lr"], g["weight_decay"], grad_div=float(world), betas=g["betas"], eps=g["eps"])
 
     def zero_grad(self, set_to_none: bool = True):
         # the backward kernels overwrite the flat gradient buffer on the first micro-step: nothing to clear

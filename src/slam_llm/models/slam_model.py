@@ -358,17 +358,25 @@ class slam_model(nn.Module):
     def _backward(self, grad_out):
         self.b200.backward(grad_out)
         if self.ddp_world_size > 1 and self.ddp_sync:
-            torch.distributed.all_reduce(self.b200.arena.grad)     # DDP: the one data-path collective (finetune.py:181-184)
+            # DDP: the one data-path collective (finetune.py:181-184).  In deferred mode (train_config.b200_overlap_allreduce, default on for
+            # DDP) it is asynchronous: FlatAdamW.step() records the update and the next forward applies it after the frozen encoder has been
+            # launched, so the all-reduce and the wait for the slowest rank overlap the next step's front end.
+            self.b200.allreduce_grads(async_op=self.b200.defer_update)
         self._bind_grad_views()
+
+    def state_dict(self, *args, **kwargs):
+        self.b200.flush_update()                                   # a deferred optimizer step must land before parameters are read
+        return super().state_dict(*args, **kwargs)
 
     def shadow_backward(self):
         """DDP `Join` (utils/train_utils.py:91): this rank has no batch for the micro-step while other ranks still train - contribute
         zero gradients to the step's all-reduce so that every replica applies the same update."""
+        self.b200.flush_update()
         if self.b200.micro_steps == 0:
             self.b200.arena.grad.zero_()
         self.b200.micro_steps += 1
         if self.ddp_world_size > 1 and self.ddp_sync:
-            torch.distributed.all_reduce(self.b200.arena.grad)
+            self.b200.allreduce_grads(async_op=self.b200.defer_update)
         self._bind_grad_views()
 
     # ---- decoder entry used by recipes that override forward() and call self.llm(...) themselves

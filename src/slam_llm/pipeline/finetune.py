@@ -86,6 +86,7 @@ def main(kwargs: DictConfig):
         # once from rank 0, and each step all-reduces the flat projector+LoRA gradient buffer inside model._backward.
         torch.distributed.broadcast(model.b200.arena.param.data, src=0)
         model.ddp_world_size = world_size
+        model.b200.defer_update = bool(train_config.get("b200_overlap_allreduce", True))   # async all-reduce + update applied behind the next front end
 
     logger.info("dataset_config: {}".format(dataset_config))
     dataset_train = get_preprocessed_dataset(tokenizer, dataset_config, split="train")

@@ -143,6 +143,25 @@ def test_lora_dropout_matches_oracle_given_the_same_masks():
     assert abs(loss_eval.item() - ref_eval["loss"].item()) / ref_eval["loss"].item() < 5e-3
 
 
+def test_deferred_update_is_the_same_arithmetic():
+    """defer_update: optimizer_step() records, the next forward applies it after the frozen front end; parameters after K steps are
+    bit-identical to the immediate mode, and every reader of the trainables (trainable_state) sees the update."""
+    c = CASES["tiny_dh64"]
+    _, a = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    _, b = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    b.defer_update = True
+    batch = to_dev(so.synthetic_batch(2, 32000, c["llm"].vocab, prompt_len=6, answer_len=9, left_pad=[0, 3], seed=5))
+    for _ in range(3):
+        la, _ = a.train_step(batch, lr=1e-3, weight_decay=0.01)
+        lb, _ = b.train_step(batch, lr=1e-3, weight_decay=0.01)
+        assert la.item() == lb.item()
+    assert b._pending_update is not None                     # third update still pending ...
+    sb = b.trainable_state()                                 # ... until somebody reads the trainables
+    assert b._pending_update is None
+    for k, v in a.trainable_state().items():
+        assert torch.equal(v, sb[k]), k
+
+
 def test_full_logits_eval_path_matches_oracle():
     c = CASES["tiny_dh64"]
     om, eng = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
