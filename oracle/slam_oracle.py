@@ -257,9 +257,15 @@ def log_mel_spectrogram(wav: torch.Tensor, n_mels: int = 80, dtype=torch.float32
     return (log_spec + 4.0) / 4.0
 
 
-def batch_log_mel(wavs: torch.Tensor, n_mels: int) -> torch.Tensor:
-    """[B, n] -> [B, T, n_mels] (the dataset's .permute(1, 0) + collator stacking, speech_dataset.py:103,246-249)."""
-    return torch.stack([log_mel_spectrogram(w, n_mels).permute(1, 0) for w in wavs])
+def batch_log_mel(wavs: torch.Tensor, n_mels: int, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, n] -> [B, T, n_mels] (the dataset's .permute(1, 0) + collator stacking, speech_dataset.py:103,246-249).
+    lengths (dynamic-frame recipe, speech_dataset_large.py:102-104,196-199): every utterance's log-mel is computed on ITS OWN samples
+    (own reflect padding, own max), then the collator right-pads the mel with zeros to the longest utterance of the batch."""
+    if lengths is None:
+        return torch.stack([log_mel_spectrogram(w, n_mels).permute(1, 0) for w in wavs])
+    mels = [log_mel_spectrogram(w[: int(n)], n_mels).permute(1, 0) for w, n in zip(wavs, lengths)]
+    t_max = max(m.shape[0] for m in mels)
+    return torch.stack([F.pad(m, (0, 0, 0, t_max - m.shape[0])) for m in mels])
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -472,7 +478,7 @@ class OracleModel:
         `audio_mel` [B,T,n_mels] or raw `audio_pcm` [B,n] (log-mel computed here)."""
         mel = batch.get("audio_mel")
         if mel is None:
-            mel = batch_log_mel(batch["audio_pcm"], self.enc_cfg.n_mels)
+            mel = batch_log_mel(batch["audio_pcm"], self.enc_cfg.n_mels, batch.get("audio_pcm_lengths"))
         dtype = self.llm_w["lm_head.weight"].dtype
         mel = mel.to(dtype)
         with torch.no_grad():                                            # encoder frozen (slam_model.py:110-113)

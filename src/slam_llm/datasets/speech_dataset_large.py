@@ -119,7 +119,8 @@ class MultiTaskDataset(IterableDataset):
             return torch.stack([self.pad(s[field], width, fill) for s in samples])
 
         batch = {"input_ids": right_padded("input_ids", self.tokenizer.pad_token_id), "attention_mask": right_padded("attention_mask", False)}
-        batch.update(common.collate_audio(samples, self.input_type, even_frames=True))
+        # PCM right-padded to the longest utterance: the step's log-mel then has max(n_i // 160) frames, exactly the reference's padded mel width
+        batch.update(common.collate_audio(samples, self.input_type))
         batch["modality_mask"] = common.span_mask(batch["attention_mask"], [0] * len(samples), [s["audio_length"] for s in samples])
         if self.inference_mode:
             batch["keys"] = [s["key"] for s in samples]

@@ -50,6 +50,14 @@ CASES = {
     "realwidth": dict(enc=(128, 1500, 1280, 20, 1), llm=(128256, 4096, 1, 32, 8, 14336, 500000.0, 1e-5), lora=(16, 32, ("q_proj", "v_proj")),
                       proj=("linear", 5, 2048), seed=1618, lr=1e-4, wd=0.0),
 }
+# dynamic-frame recipe (datasets/speech_dataset_large.py): natural-length utterances (odd and even frame counts), right padding only,
+# batches formed by the window rule (:259-263) with a 260-token budget; the step runs on the first batch with >= 3 utterances
+CASES["tiny_dynamic"] = dict(CASES["tiny"], seed=4242)
+DYNAMIC = dict(max_frame_length=260,
+               utts=[(0.6131, "ASR", "ab"), (1.5075, "ST", "hello there"), (2.2506, "ASR", "c"), (0.9519, "ASR", "lorem ipsum"), (1.8107, "ST", "x y z"),
+                     (31.0, "ASR", "dropped: longer than max_audio_length"), (0.4006, "ASR", "q")],
+               prompts={"ASR": "Transcribe. ", "ST": "Translate the speech to German. "})
+
 UTTERANCES = {   # (seconds, target text, prompt) — two prompts so the collator left-pads (speech_dataset.py:224-236)
     "tiny": [(1.30, "hello world", "Transcribe. "), (2.05, "a b", "Transcribe speech to text. "), (0.70, "the quick brown fox", "Transcribe. ")],
     "tiny_cov1d_all": [(0.9, "x", "Say it. "), (1.6, "lorem ipsum dolor", "Transcribe the speech. ")],
@@ -90,6 +98,33 @@ def reference_batch(case, tmp, mods, tokenizer):
         ds = mods["speech_dataset"].get_speech_dataset(dc, tokenizer, "train")
         samples.append(ds[0])
     return ds.collator(samples), pcm
+
+
+def dynamic_batches(case, tmp, mods, tokenizer):
+    """scp dir + prompt file on disk -> the reference MultiTaskDataset / MultiTaskDynamicBatchDataset iteration and collator."""
+    g = torch.Generator().manual_seed(CASES[case]["seed"] + 7)
+    scp = os.path.join(tmp, "scp")
+    os.makedirs(scp)
+    pcm = []
+    with open(os.path.join(scp, "multitask.jsonl"), "w") as f:
+        for i, (secs, task, target) in enumerate(DYNAMIC["utts"]):
+            n = int(round(secs * 16000))
+            p = (torch.randn(n, generator=g) * 0.1 * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+            pcm.append(p)
+            wav = os.path.join(tmp, f"dyn{i}.wav")
+            ref_glue.write_wav(wav, p.numpy())
+            f.write(json.dumps({"key": f"dyn{i}", "task": task, "target": target, "path": wav}) + "\n")
+    pp = os.path.join(tmp, "prompts.jsonl")
+    with open(pp, "w") as f:
+        for task, prompt in DYNAMIC["prompts"].items():
+            f.write(json.dumps({"task": task, "prompt": prompt}) + "\n")
+    dc = OmegaConf.create(dict(train_scp_file_path=scp, dev_scp_file_path=scp, test_scp_file_path=scp, multitask_prompt_path=pp, append_info_tasks=[],
+                               prompt_style="USER: {}\n ASSISTANT:", mel_size=CASES[case]["enc"][0], input_type="mel", pad_or_trim=False, max_audio_length=30,
+                               train_max_frame_length=DYNAMIC["max_frame_length"], eval_max_frame_length=DYNAMIC["max_frame_length"]))
+    ds = mods["speech_dataset_large"].get_speech_dataset(dc, tokenizer, "train")
+    groups = [list(items) for items in ds]
+    batches = [ds.collator(items) for items in groups]
+    return batches, pcm
 
 
 def synthetic_batch(case):
@@ -164,7 +199,20 @@ def reference_step(case: str) -> dict:
     tokenizer = ref_glue.CharTokenizer(llm.vocab)
     torch.manual_seed(0)
     with tempfile.TemporaryDirectory() as tmp:
-        if case in UTTERANCES:
+        all_batches = None
+        if case == "tiny_dynamic":
+            all_batches, pcm_all = dynamic_batches(case, tmp, mods, tokenizer)
+            pick = next(i for i, b in enumerate(all_batches) if b["input_ids"].shape[0] >= 3)
+            batch = all_batches[pick]
+            used, seen = [], 0                                       # utterances of the picked batch, in dataset order (the 31 s one is dropped)
+            kept = [i for i, (secs, _, _) in enumerate(DYNAMIC["utts"]) if secs <= 30]
+            for bi, b in enumerate(all_batches):
+                n = b["input_ids"].shape[0]
+                if bi == pick:
+                    used = kept[seen: seen + n]
+                seen += n
+            pcm = [pcm_all[i] for i in used]
+        elif case in UTTERANCES:
             batch, pcm = reference_batch(case, tmp, mods, tokenizer)
         else:
             batch, pcm = synthetic_batch(case), None
@@ -188,6 +236,11 @@ def reference_step(case: str) -> dict:
     out = dict(case=case, cfg=dict(enc=c["enc"], llm=c["llm"], lora=c["lora"], proj=c["proj"], seed=c["seed"], lr=c["lr"], wd=c["wd"]),
                loss=outputs.loss.item(), acc=float(acc), n_labels=int(rows.sum()),
                batch={k: v.clone() for k, v in batch.items() if torch.is_tensor(v) and k not in ("audio_mel", "audio_pcm")})
+    if all_batches is not None:
+        out["all_batches"] = [{k: v.clone() for k, v in b.items() if torch.is_tensor(v) and k != "audio_mel"} for b in all_batches]
+        out["all_pcm_int16"] = pcm_all
+        out["dynamic"] = DYNAMIC
+        out["mel_frames"] = int(batch["audio_mel"].shape[1])
     if pcm is not None:
         out["pcm_int16"] = pcm
     else:

@@ -32,10 +32,14 @@ def batch_of(fix) -> dict:
     what whisper.load_audio + pad_or_trim fed the reference's log-mel)."""
     b = {k: v.clone() for k, v in fix["batch"].items() if k in ("input_ids", "labels", "attention_mask", "modality_mask")}
     if "pcm_int16" in fix:
-        pcm = torch.zeros(len(fix["pcm_int16"]), 480000)
+        dynamic = "dynamic" in fix                                   # natural lengths, right-padded to the longest (speech_dataset_large.py)
+        width = max(p.numel() for p in fix["pcm_int16"]) if dynamic else 480000
+        pcm = torch.zeros(len(fix["pcm_int16"]), width)
         for i, p in enumerate(fix["pcm_int16"]):
             pcm[i, : p.numel()] = p.float() / 32768.0
         b["audio_pcm"] = pcm
+        if dynamic:
+            b["audio_pcm_lengths"] = torch.tensor([p.numel() for p in fix["pcm_int16"]], dtype=torch.int32)
     else:
         _, llm, _, _ = cfgs(fix)
         syn = so.synthetic_batch(b["input_ids"].shape[0], 480000, llm.vocab, prompt_len=24, answer_len=76, seed=fix["batch_seed"])

@@ -311,6 +311,18 @@ def _whisper_log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0, devi
     return (log_spec + 4.0) / 4.0
 
 
+def _kaldiio_module() -> types.ModuleType:
+    """kaldiio.load_mat(path) -> (rate, int16 samples): the stand-in reads a 16 kHz int16 WAV instead of an ark entry."""
+    m = types.ModuleType("kaldiio")
+
+    def load_mat(path):
+        from scipy.io import wavfile
+        rate, data = wavfile.read(path)
+        return rate, data
+    m.load_mat = load_mat
+    return m
+
+
 def _whisper_module() -> types.ModuleType:
     m = types.ModuleType("whisper")
     m.load_model, m.load_audio, m.pad_or_trim, m.log_mel_spectrogram = (_whisper_load_model, _whisper_load_audio, _whisper_pad_or_trim,
@@ -347,7 +359,7 @@ def install(extra_stubs: Iterable[str] = ()) -> None:
     assert not _iu.is_peft_available() and not _iu.is_soundfile_available()           # lru_cached: stays False once the stand-ins exist
     sys.path[:] = [p for p in sys.path if os.path.abspath(p) != os.path.join(ROOT, "src")]
     sys.path.insert(0, REFERENCE_SRC)
-    for mk in (_peft_module, _whisper_module):
+    for mk in (_peft_module, _whisper_module, _kaldiio_module):
         m = mk()
         m.__spec__ = importlib.machinery.ModuleSpec(m.__name__, None)
         sys.modules.setdefault(m.__name__, m)
@@ -356,7 +368,7 @@ def install(extra_stubs: Iterable[str] = ()) -> None:
             importlib.import_module("omegaconf")
         except ImportError:
             _load_by_path("omegaconf", os.path.join(ROOT, "src", "slam_llm", "_compat", "omegaconf_shim.py"))
-    for name in ("soundfile", "deepspeed", "deepspeed.utils", "deepspeed.utils.zero_to_fp32", "kaldiio") + tuple(extra_stubs):
+    for name in ("soundfile", "deepspeed", "deepspeed.utils", "deepspeed.utils.zero_to_fp32") + tuple(extra_stubs):
         if name not in sys.modules:
             try:
                 importlib.import_module(name)

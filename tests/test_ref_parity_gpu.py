@@ -29,7 +29,8 @@ def _step_vs_fixture(fix, small: bool):
     eng = build_engine(fix, om)
     batch = rf.batch_of(fix)
     gb = {k: v.cuda() for k, v in batch.items()}
-    mel = eng.log_mel(gb["audio_pcm"])
+    mel = eng.log_mel(gb["audio_pcm"], gb.get("audio_pcm_lengths"))
+    assert tuple(mel.shape) == tuple(fix["mel"]["shape"])
     assert (mel.flatten()[: fix["mel"]["head"].numel()].cpu() - fix["mel"]["head"]).abs().max().item() < 2e-3
     assert abs(mel.norm().item() - fix["mel"]["norm"]) / fix["mel"]["norm"] < 2e-3
     enc_out = eng.encoder.forward(mel)
@@ -94,8 +95,10 @@ def _step_vs_fixture(fix, small: bool):
             assert rf.cosine(upd, upd_ref) > 0.9, (k, rf.cosine(upd, upd_ref))
 
 
-@pytest.mark.parametrize("name", ["ref_tiny.pt", "ref_tiny_cov1d_all.pt"])
+@pytest.mark.parametrize("name", ["ref_tiny.pt", "ref_tiny_cov1d_all.pt", "ref_tiny_dynamic.pt"])
 def test_cuda_step_matches_reference_run(name):
+    """ref_tiny_dynamic: the dynamic-frame recipe (speech_dataset_large.py) - natural-length utterances (61 / 150 / 225 mel frames), each
+    log-mel on its own length, zero-padded mel frames attending freely in the encoder (reference quirk Q9), right padding only."""
     _step_vs_fixture(rf.load(name), small=True)
 
 

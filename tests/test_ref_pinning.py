@@ -25,7 +25,7 @@ def _oracle_vs_fixture(fix, small: bool):
     om = rf.oracle_model(fix)
     batch = rf.batch_of(fix)
     enc, llm, lora, proj = rf.cfgs(fix)
-    mel = so.batch_log_mel(batch["audio_pcm"], enc.n_mels)
+    mel = so.batch_log_mel(batch["audio_pcm"], enc.n_mels, batch.get("audio_pcm_lengths"))
     # log-mel: the reference run used the whisper stand-in with the filterbank from transformers.audio_utils (independent of the oracle's)
     assert tuple(mel.shape) == tuple(fix["mel"]["shape"])
     assert (mel.flatten()[: fix["mel"]["head"].numel()] - fix["mel"]["head"]).abs().max().item() < 5e-5
@@ -68,7 +68,7 @@ def _oracle_vs_fixture(fix, small: bool):
         assert bad < 0.01, (k, bad)
 
 
-@pytest.mark.parametrize("name", ["ref_tiny.pt", "ref_tiny_cov1d_all.pt"])
+@pytest.mark.parametrize("name", ["ref_tiny.pt", "ref_tiny_cov1d_all.pt", "ref_tiny_dynamic.pt"])
 def test_oracle_matches_reference_run(name):
     _oracle_vs_fixture(rf.load(name), small=True)
 
@@ -140,11 +140,48 @@ def test_dataset_mirror_reproduces_the_reference_batch(tmp_path):
             assert (got["audio_mel"].flatten()[:512] - fix["mel"]["head"]).abs().max().item() < 5e-5
 
 
+def test_dynamic_dataset_mirror_reproduces_the_reference_batches(tmp_path):
+    """scp dir -> this repo's MultiTaskDataset / MultiTaskDynamicBatchDataset gives the same batches (window rule, ids, labels, masks) as the
+    reference's, the too-long utterance dropped, PCM + lengths in place of the CPU mel with exactly the reference's padded mel width."""
+    import json
+    import numpy as np
+    from scipy.io import wavfile
+    from omegaconf import OmegaConf
+    from slam_llm.datasets.speech_dataset_large import get_speech_dataset
+    from ref_glue import CharTokenizer
+    fix = rf.load("ref_tiny_dynamic.pt")
+    dyn = fix["dynamic"]
+    scp = tmp_path / "scp"
+    scp.mkdir()
+    with open(scp / "multitask.jsonl", "w") as f:
+        for i, ((secs, task, target), p) in enumerate(zip(dyn["utts"], fix["all_pcm_int16"])):
+            wav = str(tmp_path / f"d{i}.wav")
+            wavfile.write(wav, 16000, p.numpy().astype(np.int16))
+            f.write(json.dumps({"key": f"dyn{i}", "task": task, "target": target, "path": wav}) + "\n")
+    pp = tmp_path / "prompts.jsonl"
+    pp.write_text("".join(json.dumps({"task": t, "prompt": p}) + "\n" for t, p in dyn["prompts"].items()))
+    dc = OmegaConf.create(dict(train_scp_file_path=str(scp), dev_scp_file_path=str(scp), test_scp_file_path=str(scp), multitask_prompt_path=str(pp),
+                               append_info_tasks=[], prompt_style="USER: {}\n ASSISTANT:", mel_size=80, input_type="mel", pad_or_trim=False,
+                               max_audio_length=30, train_max_frame_length=dyn["max_frame_length"], eval_max_frame_length=dyn["max_frame_length"]))
+    ds = get_speech_dataset(dc, CharTokenizer(512), "train")
+    got = [ds.collator(items) for items in ds]
+    assert len(got) == len(fix["all_batches"])
+    for g, r in zip(got, fix["all_batches"]):
+        for k in ("input_ids", "labels", "attention_mask", "modality_mask"):
+            assert torch.equal(g[k].to(r[k].dtype), r[k]), k
+        assert torch.equal(g["audio_mel_post_mask"].float(), r["audio_mel_post_mask"].float())
+        assert g["audio_pcm"].shape[1] // 160 == 2 * r["audio_mel_post_mask"].shape[1] - (1 if (g["audio_pcm"].shape[1] // 160) % 2 else 0)
+    picked = next(g for g, r in zip(got, fix["all_batches"]) if torch.equal(r["input_ids"], fix["batch"]["input_ids"]))
+    want = rf.batch_of(fix)
+    assert torch.equal(picked["audio_pcm"], want["audio_pcm"]) and torch.equal(picked["audio_pcm_lengths"], want["audio_pcm_lengths"])
+    assert picked["audio_pcm"].shape[1] // 160 == fix["mel_frames"]
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/slam_llm"), reason="/root/reference is only present in the build container")
 def test_fixtures_regenerate_from_the_reference_code():
     """Re-run the reference's own code (dedicated process: its `slam_llm` package shadows this repo's mirror) and compare with the
     committed fixtures.  The real-width case is left to `make_ref_golden.py --check --only realwidth` (3 min)."""
-    for only in ("tiny", "collator"):
+    for only in ("tiny", "collator"):          # "tiny" matches ref_tiny, ref_tiny_cov1d_all and ref_tiny_dynamic
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_ref_golden.py"), "--check", "--only", only],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
