@@ -39,6 +39,11 @@ WORKLOADS = {
                name="whisper-large-v3+llama-3-8b lora(r=16,q/v) linear-proj k=5, 4x30s utt per GPU (120 audio-s/step/GPU), S=401"),
     "c2": dict(enc="base", llm="llama-3-8b", r=16, alpha=32, targets=("q_proj", "v_proj"), batch=4, seconds=30, prompt=24, answer=76,
                name="whisper-base+llama-3-8b lora(r=16,q/v) linear-proj k=5, 4x30s utt per GPU (120 audio-s/step/GPU), S=401"),
+    # BASELINE configs[2] batching: utterances U[10 s, 30 s] grouped by the reference's window rule (speech_dataset_large.py:259-263,
+    # train_max_frame_length tokens per batch), natural lengths, right padding; value counts REAL audio seconds
+    "c3-dynamic": dict(enc="large-v3", llm="llama-3-8b", r=16, alpha=32, targets=("q_proj", "v_proj"), batch=None, seconds=(10, 30), prompt=24, answer=76,
+                       max_frame_length=1500, n_batches=8,
+                       name="whisper-large-v3+llama-3-8b lora(r=16,q/v) linear-proj k=5, dynamic-frame batches (utt U[10,30] s, window rule 1500 tokens)"),
     "tiny": dict(enc="tiny", llm="tinyllama-1.1b", r=8, alpha=32, targets=("q_proj", "v_proj"), batch=1, seconds=30, prompt=24, answer=76,
                  name="whisper-tiny+tinyllama-1.1b lora(r=8,q/v), 1x30s"),
 }
@@ -63,6 +68,50 @@ def make_batch(wl, vocab, seed, pin=False):
     if pin:
         batch = {k: v.pin_memory() for k, v in batch.items()}
     return batch, S
+
+
+def make_dynamic_batches(wl, vocab, seed, pin=False):
+    """Synthetic stream of natural-length utterances grouped by the reference window rule; right-padding collator contract of
+    speech_dataset_large.py:180-233 (audio first, no left padding) with raw PCM + per-utterance lengths (GPU front end)."""
+    g = torch.Generator().manual_seed(seed)
+    lo, hi = wl["seconds"]
+    batches, buf = [], []
+
+    def tokens(n):
+        return ((n // 160 + 1) // 2) // 5 + wl["prompt"] + wl["answer"] + 1
+
+    def flush(items):
+        B = len(items)
+        S = max(tokens(n) for n in items)
+        width = max(items)
+        ids = torch.zeros(B, S, dtype=torch.int64)
+        labels = torch.full((B, S), -100, dtype=torch.int64)
+        att = torch.zeros(B, S, dtype=torch.bool)
+        mod = torch.zeros(B, S, dtype=torch.bool)
+        pcm = torch.zeros(B, width)
+        for b, n in enumerate(items):
+            ta = ((n // 160 + 1) // 2) // 5
+            nt = tokens(n)
+            ids[b, ta:nt] = torch.randint(0, vocab, (nt - ta,), generator=g)
+            ids[b, :ta] = -1
+            labels[b, ta + wl["prompt"]:nt] = ids[b, ta + wl["prompt"]:nt]
+            att[b, :nt] = True
+            mod[b, :ta] = True
+            pcm[b, :n] = torch.randn(n, generator=g) * 0.1
+        batch = dict(input_ids=ids, labels=labels, attention_mask=att, modality_mask=mod, audio_pcm=pcm,
+                     audio_pcm_lengths=torch.tensor(items, dtype=torch.int32))
+        if pin:
+            batch = {k: v.pin_memory() for k, v in batch.items()}
+        return batch, sum(items) / 16000.0, B * width / 16000.0
+
+    while len(batches) < wl["n_batches"]:
+        n = int(torch.randint(lo * 16000, hi * 16000 + 1, (1,), generator=g))
+        longest = max([tokens(n)] + [tokens(m) for m in buf])
+        if buf and (len(buf) + 1) * longest > wl["max_frame_length"]:
+            batches.append(flush(buf))
+            buf = []
+        buf.append(n)
+    return batches
 
 
 class ClockSampler:
@@ -216,17 +265,112 @@ def cpu_reference(wl, steps, warmup, budget_s=150.0, quiet=True):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# the recipe surface: model built by setup_encoder / setup_llm / setup_encoder_projector + slam_model, driven by train()
+# ----------------------------------------------------------------------------------------------------------------------
+def build_recipe_model(wl, enc, llm, lora, world):
+    """What a recipe's model_factory does (examples/asr_librispeech/model/slam_model_asr.py:15-55) minus the tokenizer download: a config.json
+    of the LLM architecture in a temp dir, `b200_random_init` for the frozen weights (no checkpoints offline), LoRA B ~ N(0, 0.02) so that
+    dA != 0 (peft would zero-init B)."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "src"))
+    import slam_llm  # noqa: F401  (installs the omegaconf / hydra / whisper shims when the real packages are absent)
+    from omegaconf import OmegaConf
+    from slam_llm.models.slam_model import setup_encoder, setup_encoder_projector, setup_llm, slam_model
+    tmp = tempfile.mkdtemp(prefix="slam_bench_llm_")
+    json.dump(dict(model_type="llama", vocab_size=llm.vocab, hidden_size=llm.d, intermediate_size=llm.ffn, num_hidden_layers=llm.layers,
+                   num_attention_heads=llm.heads, num_key_value_heads=llm.kv_heads, rms_norm_eps=llm.eps, rope_theta=llm.rope_theta),
+              open(os.path.join(tmp, "config.json"), "w"))
+    train_config = OmegaConf.create(dict(
+        model_name="bench", enable_fsdp=False, enable_ddp=False, enable_deepspeed=False, quantization=False, freeze_llm=True, freeze_encoder=True,
+        use_peft=True, seed=42, num_epochs=1, batching_strategy="custom", gradient_accumulation_steps=1, run_validation=False, validation_interval=10 ** 9,
+        save_model=False, use_fp16=False, lr=1e-4, weight_decay=0.0, warmup_steps=1000, total_steps=100000, output_dir=tmp,
+        peft_config=dict(peft_method="lora", r=lora.r, lora_alpha=lora.alpha, target_modules=list(lora.targets), bias="none", task_type="CAUSAL_LM",
+                         lora_dropout=0.0, inference_mode=False)))
+    model_config = OmegaConf.create(dict(llm_name=wl["llm"], llm_path=tmp, llm_dim=llm.d, encoder_name="whisper", encoder_path=wl["enc"], encoder_dim=enc.d,
+                                         encoder_projector="linear", encoder_projector_ds_rate=5, b200_random_init=True))
+    encoder = setup_encoder(train_config, model_config)
+    llm_mod = setup_llm(train_config, model_config)
+    projector = setup_encoder_projector(train_config, model_config)
+    model = slam_model(encoder, llm_mod, projector, None, train_config, model_config, metric="acc")
+    model.b200.llm.init_lora(None, seed=44, b_std=0.02)
+    return model, train_config
+
+
+class _SyntheticUtterances(torch.utils.data.Dataset):
+    """Map-style dataset of synthetic utterances in the item layout of datasets/speech_dataset.py:109-161 ([audio(-1)*L, prompt, answer, eos]),
+    a fresh waveform per item; batches are formed by the repo's SpeechDatasetJsonl.collator (the reference collator contract)."""
+
+    def __init__(self, wl, vocab, n_items, seed):
+        from slam_llm.datasets.speech_dataset import SpeechDatasetJsonl
+        self.wl, self.vocab, self.n, self.seed = wl, vocab, n_items, seed
+        c = SpeechDatasetJsonl.__new__(SpeechDatasetJsonl)
+        c.tokenizer = type("Tok", (), {"pad_token_id": 0, "eos_token_id": 2})()
+        c.input_type, c.inference_mode = "mel", False
+        self._collator = c
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 100003 + i)
+        n = self.wl["seconds"] * 16000
+        ta = ((n // 160 + 1) // 2) // 5
+        text = torch.randint(3, self.vocab, (self.wl["prompt"] + self.wl["answer"] + 1,), generator=g)
+        ids = torch.cat((torch.full((ta,), -1), text))
+        labels = ids.clone()
+        labels[: ta + self.wl["prompt"]] = -100
+        att = ids.ge(-1)
+        return dict(input_ids=ids, labels=labels, attention_mask=att, audio=None, audio_mel=None, audio_pcm=torch.randn(n, generator=g) * 0.1,
+                    audio_length=ta, prompt_length=self.wl["prompt"])
+
+    def collator(self, samples):
+        return self._collator.collator(samples)
+
+
+def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup):
+    """`e2e_recipe`: slam_llm.utils.train_utils.train() (the reference's loop, utils/train_utils.py:46-392) over a DataLoader (2 workers, pinned
+    memory) of FRESH synthetic batches: collate, H2D, label rows, model(**batch), outputs.loss.backward(), FlatAdamW.step(), LambdaLR.step(), the
+    per-step tqdm description (one D2H read per step).  Wall-clock around the whole epoch of `steps` batches, device synchronised on both sides."""
+    from omegaconf import OmegaConf
+    from slam_llm.utils.train_utils import train
+    from slam_llm_b200.optim import FlatAdamW
+    log_config = OmegaConf.create(dict(use_wandb=False, log_interval=10))
+    optimizer = FlatAdamW(model, lr=train_config.lr, weight_decay=train_config.weight_decay)
+    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda step: min((step + 1) / train_config.warmup_steps, 1))
+
+    def epoch(n_batches, seed):
+        ds = _SyntheticUtterances(wl, llm.vocab, n_batches * wl["batch"], seed)
+        dl = torch.utils.data.DataLoader(ds, batch_size=wl["batch"], num_workers=2, pin_memory=True, collate_fn=ds.collator, drop_last=True,
+                                         persistent_workers=False, prefetch_factor=4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = train(model, dl, None, None, optimizer, scheduler, 1, train_config, log_config)
+        model.b200.flush_update()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, res
+
+    epoch(max(warmup, 3), seed=1)
+    t, res = epoch(steps, seed=2)
+    ms = t * 1e3 / steps
+    return {"value": round(audio_s / (ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
+            "path": "slam_llm.utils.train_utils.train() + DataLoader(2 workers, fresh batch per step) + FlatAdamW + LambdaLR; wall clock incl. worker start-up",
+            "avg_train_loss": round(float(res["avg_train_loss"]), 4)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # B-EAGER: the reference's eager HF/PEFT step on the same GPU, same batch (baseline/eager_hf.py); N=1 only
 # ----------------------------------------------------------------------------------------------------------------------
-def eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, our_e2e, steps=20, warmup=5):
+def eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, our_e2e, steps=20, warmup=5, model=None):
     """Frees this repo's engine state, builds HF WhisperEncoder + LlamaForCausalLM (fp32 master weights) with restated peft LoRA, and times the
     reference train-loop body (fp16 autocast + GradScaler + AdamW, train_utils.py:112-149) on the same synthetic batch; the log-mel the
     reference computes in its DataLoader workers is prepared outside the timed region (generous to the baseline)."""
     try:
         from baseline import eager_hf
         mel = eng.log_mel(host_batch["audio_pcm"].to(dev)).float().cpu()
-        for k in list(vars(eng)):
+        for k in list(vars(eng)):                                   # drop every device tensor the step owns (the recipe modules only hold views)
             setattr(eng, k, None)
+        if model is not None:
+            model.encoder.b200 = model.llm.b200 = model.b200 = None
         import gc
         gc.collect()
         torch.cuda.empty_cache()
@@ -331,14 +475,32 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     enc, llm = C.WHISPER[wl["enc"]], C.LLM[wl["llm"]]
     lora, proj = C.LoraCfg(wl["r"], wl["alpha"], tuple(wl["targets"])), C.ProjCfg("linear", 5, 2048)
-    eng = SlamStepB200(enc, llm, lora, proj, device=dev, seed=42, lora_b_std=0.02)
+    model, train_config = build_recipe_model(wl, enc, llm, lora, world)   # the recipe surface (setup_* + slam_model) builds the step
+    eng = model.b200
     eng.defer_update = world > 1 and args.overlap == 1      # async gradient all-reduce, update applied behind the next step's frozen front end
-    host_batch, S = make_batch(wl, llm.vocab, seed=42 + rank, pin=True)
-    rows, tgts = SlamStepB200.label_rows(host_batch["labels"])
-    host_batch["_rows"], host_batch["_targets"] = rows.pin_memory(), tgts.pin_memory()
-    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
-    B = wl["batch"]
-    audio_s = B * wl["seconds"]
+    if wl["batch"] is None:
+        if args.steps % wl["n_batches"]:
+            raise SystemExit(f"--workload {args.workload}: --steps must be a multiple of {wl['n_batches']} (every step runs a different batch of the cycle)")
+        dyn = make_dynamic_batches(wl, llm.vocab, seed=42 + rank, pin=True)
+        host_batches = [b for b, _, _ in dyn]
+        audio_s = sum(real for _, real, _ in dyn) / len(dyn)          # REAL audio seconds per step (mean over the cycle, this rank)
+        padded_s = sum(pad for _, _, pad in dyn) / len(dyn)
+        B, S = max(b["input_ids"].shape[0] for b in host_batches), max(b["input_ids"].shape[1] for b in host_batches)
+    else:
+        hb, S = make_batch(wl, llm.vocab, seed=42 + rank, pin=True)
+        host_batches = [hb]
+        B = wl["batch"]
+        audio_s = padded_s = B * wl["seconds"]
+    n_rows = 0
+    for hb in host_batches:
+        rows, tgts = SlamStepB200.label_rows(hb["labels"])
+        hb["_rows"], hb["_targets"] = rows.pin_memory(), tgts.pin_memory()
+        n_rows += rows.numel()
+    n_rows //= len(host_batches)
+    host_batch = host_batches[0]
+    dev_batches = [{k: v.to(dev) for k, v in hb.items()} for hb in host_batches]
+    dev_batch = dev_batches[0]
+    counter = {"i": 0}
     lr = 1e-4
 
     def barrier():
@@ -347,10 +509,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        return eng.train_step(dev_batch, lr=lr, world_size=world)
+        counter["i"] += 1
+        return eng.train_step(dev_batches[counter["i"] % len(dev_batches)], lr=lr, world_size=world)
 
     def step_e2e():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
+        counter["i"] += 1
+        b = {k: v.to(dev, non_blocking=True) for k, v in host_batches[counter["i"] % len(host_batches)].items()}
         loss, acc = eng.train_step(b, lr=lr, world_size=world)
         return loss.item()                                            # D2H read of the step's result
 
@@ -412,7 +576,7 @@ def run_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms2 = t.item()
     e2e_value = world * audio_s / (ms2 / args.steps / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
+    h2d = sum(v.numel() * v.element_size() for hb in host_batches for v in hb.values()) // len(host_batches)
 
     if args.breakdown:
         scale_breakdown(args, eng, dev_batch, lr, rank, world, dev)
@@ -421,7 +585,7 @@ def run_ours(args):
             torch.distributed.destroy_process_group()
         return
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    fl = C.step_flops(enc, llm, proj, lora, B, wl["seconds"] * 100, S, n_label_rows=rows.numel())
+    fl = C.step_flops(enc, llm, proj, lora, B, int(padded_s / B * 100), S, n_label_rows=n_rows)
     achieved = gemm_flops / max(gemm_ms, 1e-9) / 1e9                  # TFLOP/s over all tcgen05 GEMM launches of the timed steps
     roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step: base, fused LoRA, dgrad, wgrad, lm_head)",
             "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
@@ -435,9 +599,15 @@ def run_ours(args):
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    recipe = None
+    if world == 1 and wl["batch"] is not None and not args.skip_recipe:
+        try:
+            recipe = recipe_leg(wl, model, train_config, llm, audio_s, args.steps, args.warmup)
+        except Exception as e:
+            recipe = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     eager = None
-    if world == 1 and not args.skip_eager:
-        eager = eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, e2e_value)
+    if world == 1 and not args.skip_eager and wl["batch"] is not None:
+        eager = eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, e2e_value, model=model)
     cb = None
     if world == 1 and not args.skip_cpu:
         cb, _ = cpu_reference(wl, steps=2, warmup=0, budget_s=25.0)
@@ -446,13 +616,14 @@ def run_ours(args):
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                       "audio_s_per_step_per_gpu": {"real": round(audio_s, 2), "padded": round(padded_s, 2)},
                        "grad_allreduce": ("none" if world == 1 else "async NCCL all-reduce of the flat fp32 arena, AdamW deferred behind the next step's frozen front end"
                                           if eng.defer_update else "blocking NCCL all-reduce of the flat fp32 arena"),
                        "l2": "per-step working set (35 GB bf16 weights streamed from HBM) >> 126 MB L2; no flush needed",
                        "lm_head_rows": "rows with a label only (loss/grad identical to full logits; eval path computes all rows)"},
             "clocks": clocks, "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                                       "ms_per_step": round(ms2 / args.steps, 3)},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "eager_gpu_baseline": eager, "loss": round(final_loss, 4)}
+            "e2e_recipe": recipe, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "eager_gpu_baseline": eager, "loss": round(final_loss, 4)}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -469,6 +640,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="N>1: 1 = async all-reduce + deferred AdamW (default), 0 = blocking all-reduce")
     ap.add_argument("--breakdown", action="store_true", help="N>1 diagnostic: per-rank step time without / with blocking / with overlapped all-reduce "
                                                               "-> gpurun_out/scale_breakdown_n{N}.json")
+    ap.add_argument("--skip-recipe", action="store_true", help="skip the e2e_recipe leg (train() + DataLoader)")
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-HF-on-GPU baseline leg (B-EAGER)")
     args = ap.parse_args()
     if args.impl == "reference":
