@@ -393,6 +393,10 @@ def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
     power/thermal envelope), (b) blocking all-reduce after backward (round-1 design), (c) async all-reduce + deferred AdamW.  Also the host
     enqueue time per step and, for (b), the device time spent inside the all-reduce (which includes waiting for the slowest rank)."""
     import torch.distributed as dist
+    if world == 1:
+        class dist:  # noqa: N801  (single process: no collectives)
+            barrier = staticmethod(lambda: None)
+            all_gather_object = staticmethod(lambda out, obj: out.__setitem__(0, obj))
 
     def run(mode):
         eng.flush_update()
@@ -427,7 +431,28 @@ def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
             out["allreduce_ms_per_step"] = sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events)
         return out
 
-    res = {m: run(m) for m in ("independent", "blocking", "overlap")}
+    def host_only():
+        """Pure host cost of enqueueing one step: device idle and launch queue empty at the start, no synchronisation inside."""
+        eng.flush_update()
+        eng.defer_update = False
+        ts = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.forward(dev_batch, train=True)
+            t1 = time.perf_counter()
+            eng.backward()
+            t2 = time.perf_counter()
+            eng.optimizer_step(lr, 0.0)
+            t3 = time.perf_counter()
+            ts.append((t1 - t0, t2 - t1, t3 - t2))
+        torch.cuda.synchronize()
+        best = min(ts, key=sum)
+        return {"forward_ms": best[0] * 1e3, "backward_ms": best[1] * 1e3, "optimizer_ms": best[2] * 1e3, "total_ms": sum(best) * 1e3}
+
+    modes = ("independent", "blocking", "overlap") if world > 1 else ("independent",)
+    res = {m: run(m) for m in modes}
+    res["host_only"] = host_only()
     try:
         smi = subprocess.run(["nvidia-smi", f"--id={dev.index}", "--query-gpu=clocks.sm,power.draw,temperature.gpu", "--format=csv,noheader,nounits"],
                              capture_output=True, text=True, timeout=10).stdout.strip()
@@ -437,7 +462,8 @@ def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     if rank == 0:
-        summary = {m: {"max_ms": max(g[m]["ms_per_step"] for g in gathered), "min_ms": min(g[m]["ms_per_step"] for g in gathered)} for m in ("independent", "blocking", "overlap")}
+        summary = {m: {"max_ms": max(g[m]["ms_per_step"] for g in gathered), "min_ms": min(g[m]["ms_per_step"] for g in gathered)} for m in modes}
+        summary["host_only_total_ms"] = {"max": max(g["host_only"]["total_ms"] for g in gathered), "min": min(g["host_only"]["total_ms"] for g in gathered)}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"scale_breakdown_n{world}.json"), "w") as f:
             json.dump({"world": world, "steps": steps, "summary": summary, "ranks": gathered}, f, indent=1)
@@ -471,6 +497,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from slam_llm_b200 import config as C, ops
     from slam_llm_b200.engine import SlamStepB200
+    from slam_llm_b200.graphed import signature
 
     wl = WORKLOADS[args.workload]
     enc, llm = C.WHISPER[wl["enc"]], C.LLM[wl["llm"]]
@@ -508,14 +535,40 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # one CUDA graph pair per shape bucket (slam_llm_b200/graphed.py); falls back to the eager step (and says so in `config`)
+    graphs, launch_mode = {}, "eager (ctypes launches)"
+    if args.graph == 1:
+        try:
+            from slam_llm_b200.graphed import GraphedTrainStep, signature
+            for db in dev_batches:
+                if signature(db) not in graphs:
+                    graphs[signature(db)] = GraphedTrainStep(eng, db)
+            launch_mode = f"cuda-graph replay (2 graphs/step, {len(graphs)} shape bucket(s)) + eager all-reduce/AdamW"
+        except Exception as e:
+            graphs = {}
+            launch_mode = f"eager (graph capture failed: {type(e).__name__}: {e})"[:200]
+            print("[bench] " + launch_mode, file=sys.stderr, flush=True)
+
+    def run_step(b):
+        g = graphs.get(signature(b)) if graphs else None
+        if g is not None:
+            return g.train_step(b, lr=lr, world_size=world)
+        return eng.train_step(b, lr=lr, world_size=world)
+
     def step_resident():
         counter["i"] += 1
-        return eng.train_step(dev_batches[counter["i"] % len(dev_batches)], lr=lr, world_size=world)
+        return run_step(dev_batches[counter["i"] % len(dev_batches)])
 
     def step_e2e():
         counter["i"] += 1
-        b = {k: v.to(dev, non_blocking=True) for k, v in host_batches[counter["i"] % len(host_batches)].items()}
-        loss, acc = eng.train_step(b, lr=lr, world_size=world)
+        hb = host_batches[counter["i"] % len(host_batches)]
+        g = graphs.get(signature(hb)) if graphs else None
+        if g is not None:
+            g.load(hb)                                                # pinned host -> the graph's static device buffers
+            loss, acc = g.train_step(None, lr=lr, world_size=world)
+        else:
+            b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+            loss, acc = eng.train_step(b, lr=lr, world_size=world)
         return loss.item()                                            # D2H read of the step's result
 
     for _ in range(max(args.warmup, 3)):
@@ -533,7 +586,9 @@ def run_ours(args):
     eng.flush_update()                                                # deferred mode: the K-th update lands inside the timed region
     e1.record()
     barrier()
-    launches = ops.launch_count() - l0
+    launches = ops.launch_count() - l0                                # eager launches (all of the step, or only AdamW when graphed)
+    if graphs:
+        launches += args.steps * next(iter(graphs.values())).kernels_per_step   # + the kernels each graph replay launches
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -551,7 +606,9 @@ def run_ours(args):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(args.steps):
-        step_resident()
+        counter["i"] += 1
+        eng.train_step(dev_batches[counter["i"] % len(dev_batches)], lr=lr, world_size=world)   # eager: events cannot be read out of a graph replay
+    eng.flush_update()
     g1.record()
     barrier()
     ops.set_gemm_event_log(None)
@@ -615,7 +672,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+            "config": {"workload": wl["name"], "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}", "step_launch": launch_mode,
                        "audio_s_per_step_per_gpu": {"real": round(audio_s, 2), "padded": round(padded_s, 2)},
                        "grad_allreduce": ("none" if world == 1 else "async NCCL all-reduce of the flat fp32 arena, AdamW deferred behind the next step's frozen front end"
                                           if eng.defer_update else "blocking NCCL all-reduce of the flat fp32 arena"),
@@ -637,6 +694,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay the step from CUDA graphs (default), 0 = eager ctypes launches")
     ap.add_argument("--overlap", type=int, default=1, help="N>1: 1 = async all-reduce + deferred AdamW (default), 0 = blocking all-reduce")
     ap.add_argument("--breakdown", action="store_true", help="N>1 diagnostic: per-rank step time without / with blocking / with overlapped all-reduce "
                                                               "-> gpurun_out/scale_breakdown_n{N}.json")

@@ -667,19 +667,27 @@ class SlamStepB200:
         """batch: collator contract (input_ids, labels, attention_mask, modality_mask, audio_mel | audio_pcm) on device.
         Optional precomputed '_rows' (int32) / '_targets' (int64) avoid a device->host sync.
         Returns (loss, acc, logits_or_None); loss/acc are 0-dim device tensors."""
+        enc_out = self.forward_front(batch)                                                # frozen: does not read the trainables
+        self.flush_update()                                                                # (deferred mode) all-reduce wait + AdamW of the previous step
+        return self.forward_rest(batch, enc_out, train=train, full_logits=full_logits)
+
+    def forward_front(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """log-mel (unless the batch carries audio_mel) + Whisper encoder: the part of the step that is independent of the trainables."""
         dev = self.device
-        ids = batch["input_ids"].to(dev).contiguous()
-        labels = batch["labels"].to(dev)
-        key_mask = batch["attention_mask"].to(dev).to(torch.uint8).contiguous()
-        mod_mask = batch["modality_mask"].to(dev).to(torch.uint8).contiguous()
         mel = batch.get("audio_mel")
         if mel is None:
             mel = self.log_mel(batch["audio_pcm"].to(dev, F32), batch.get("audio_pcm_lengths"))
         else:
             mel = mel.to(dev, F32)
+        return self.encoder.forward(mel)
+
+    def forward_rest(self, batch: Dict[str, torch.Tensor], enc_out: torch.Tensor, train: bool = True, full_logits: bool = False):
+        dev = self.device
+        ids = batch["input_ids"].to(dev).contiguous()
+        labels = batch["labels"].to(dev)
+        key_mask = batch["attention_mask"].to(dev).to(torch.uint8).contiguous()
+        mod_mask = batch["modality_mask"].to(dev).to(torch.uint8).contiguous()
         B, S = ids.shape
-        enc_out = self.encoder.forward(mel)                                                # frozen: does not read the trainables
-        self.flush_update()                                                                # (deferred mode) all-reduce wait + AdamW of the previous step
         self.llm.pack_lora()                                                               # adapters change every optimizer step
         self.llm.dropout_active = bool(train and self.lora_dropout_enabled and self.llm.dropout_p > 0.0)
         self.llm.dropout_step += 1

@@ -162,6 +162,33 @@ def test_deferred_update_is_the_same_arithmetic():
         assert torch.equal(v, sb[k]), k
 
 
+def test_cuda_graph_replay_is_the_same_arithmetic():
+    """GraphedTrainStep (two CUDA graphs per step) vs the eager step: same kernels on the same data -> same losses; parameters after 3 steps on
+    two alternating batches agree to fp32 atomics reordering (the split-K / LoRA wgrad reductions are atomic)."""
+    from slam_llm_b200.engine import SlamStepB200
+    from slam_llm_b200.graphed import GraphedTrainStep
+    c = CASES["tiny_dh64"]
+    _, a = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    _, b = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
+    batches = []
+    for seed in (5, 6):
+        hb = so.synthetic_batch(2, 32000, c["llm"].vocab, prompt_len=6, answer_len=9, left_pad=[0, 3], seed=seed)
+        hb["_rows"], hb["_targets"] = SlamStepB200.label_rows(hb["labels"])
+        batches.append(to_dev(hb))
+    g = GraphedTrainStep(b, batches[0])
+    assert g.kernels_per_step > 50
+    assert torch.equal(a.arena.param, b.arena.param)                      # capture + warm-up left the trainables untouched
+    for i in range(3):
+        la, _ = a.train_step(batches[i % 2], lr=1e-3, weight_decay=0.01)
+        lb, _ = g.train_step(batches[i % 2], lr=1e-3, weight_decay=0.01)
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item()), (i, la.item(), lb.item())
+    pa, pb = a.trainable_state(), b.trainable_state()
+    for k in pa:
+        assert rel_l2(pb[k], pa[k]) < 1e-4, (k, rel_l2(pb[k], pa[k]))
+    with pytest.raises(ValueError):
+        g.train_step({k: v[:1] for k, v in batches[0].items()})          # another shape bucket needs its own graph
+
+
 def test_full_logits_eval_path_matches_oracle():
     c = CASES["tiny_dh64"]
     om, eng = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
