@@ -292,7 +292,8 @@ def build_recipe_model(wl, enc, llm, lora, world):
     llm_mod = setup_llm(train_config, model_config)
     projector = setup_encoder_projector(train_config, model_config)
     model = slam_model(encoder, llm_mod, projector, None, train_config, model_config, metric="acc")
-    model.b200.llm.init_lora(None, seed=44, b_std=0.02)
+    with torch.no_grad():
+        model.b200.llm.init_lora(None, seed=44, b_std=0.02)
     return model, train_config
 
 
@@ -571,6 +572,16 @@ def run_ours(args):
             loss, acc = eng.train_step(b, lr=lr, world_size=world)
         return loss.item()                                            # D2H read of the step's result
 
+    if args.ncu_step:
+        # profiling aid: `ncu --profile-from-start off ... python bench.py --ncu-step --graph 0` captures exactly ONE eager step
+        for _ in range(3):
+            eng.train_step(dev_batch, lr=lr, world_size=world)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eng.train_step(dev_batch, lr=lr, world_size=world)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # ---------------- timed region 1: inputs resident in HBM
@@ -694,6 +705,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--ncu-step", action="store_true", help="run 3 warm-up steps, then ONE eager step between cudaProfilerStart/Stop, and exit")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the step from CUDA graphs (default), 0 = eager ctypes launches")
     ap.add_argument("--overlap", type=int, default=1, help="N>1: 1 = async all-reduce + deferred AdamW (default), 0 = blocking all-reduce")
     ap.add_argument("--breakdown", action="store_true", help="N>1 diagnostic: per-rank step time without / with blocking / with overlapped all-reduce "

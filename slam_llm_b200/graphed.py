@@ -43,7 +43,7 @@ class GraphedTrainStep:
         self.sig = signature(example_batch)
         self.static = {k: example_batch[k].to(dev).clone() for k in INPUT_KEYS if example_batch.get(k) is not None}
         eng.flush_update()
-        keep = (eng.arena.param.clone(), eng.arena.exp_avg.clone(), eng.arena.exp_avg_sq.clone(), eng.arena.step_count, eng.llm.dropout_step)
+        keep = (eng.arena.param.detach().clone(), eng.arena.exp_avg.clone(), eng.arena.exp_avg_sq.clone(), eng.arena.step_count, eng.llm.dropout_step)
         # warm-up on a side stream (allocator pools, rope tables, cudaFuncSetAttribute, scratch pools reach their steady size)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -69,7 +69,8 @@ class GraphedTrainStep:
         self.kernels_per_step = ops.launch_count() - n0            # libslam_b200 kernels recorded into the two graphs (replayed every step)
         self._keep = [_engine._THIN_POOL.buf]                       # scratch the captured kernels address: must outlive any later re-allocation
         # the warm-up steps must not count as training: restore parameters / moments (backward never touches them, but be explicit)
-        eng.arena.param.copy_(keep[0]); eng.arena.exp_avg.copy_(keep[1]); eng.arena.exp_avg_sq.copy_(keep[2])
+        with torch.no_grad():
+            eng.arena.param.copy_(keep[0]); eng.arena.exp_avg.copy_(keep[1]); eng.arena.exp_avg_sq.copy_(keep[2])
         eng.arena.step_count, eng.llm.dropout_step = keep[3], keep[4]
         torch.cuda.synchronize(dev)
 

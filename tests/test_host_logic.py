@@ -381,6 +381,28 @@ def test_reference_recipe_files_import_unchanged_against_the_mirror(monkeypatch)
     assert ft.train is main
 
 
+def test_reference_model_factory_reaches_the_b200_engine(tmp_path, monkeypatch):
+    """The reference's OWN examples/asr_librispeech/model/slam_model_asr.py:model_factory, loaded through the plugin loader exactly like
+    finetune.main does (utils/model_utils.py:4-29), runs against the mirror: tokenizer from llm_path, then setup_encoder hands over to the
+    B200 engine — which on this CPU-only box refuses loudly (no CPU fallback).  On a GPU box the same call chain is exercised by
+    tests/test_recipe_gpu.py through a plugin of the same shape (the reference file itself cannot travel to the GPU box)."""
+    import logging
+    import torch
+    from recipe_util import make_llm_dir, run_config
+    from slam_llm.utils.model_utils import get_custom_model_factory
+    if torch.cuda.is_available():
+        pytest.skip("CPU-box check of the refusal path")
+    rec = "/root/reference/examples/asr_librispeech/model/slam_model_asr.py"
+    if not os.path.isfile(rec):
+        pytest.skip("/root/reference is only present in the build container")
+    llm_dir = make_llm_dir(str(tmp_path / "llm"))
+    cfg = run_config(llm_dir, "unused.jsonl", str(tmp_path), rec + ":model_factory", "src/slam_llm/datasets/speech_dataset.py:get_speech_dataset")
+    factory = get_custom_model_factory(cfg.model_config, logging.getLogger())
+    assert factory.__module__ != "recipe_model" and factory.__code__.co_filename == rec
+    with pytest.raises(RuntimeError, match="CUDA"):
+        factory(cfg.train_config, cfg.model_config, metric="acc")
+
+
 # ------------------------------------------------------------------------------------------------- dynamic-frame batching (config 3)
 def test_dynamic_frame_dataset_window_rule_and_right_padding(tmp_path):
     from slam_llm.datasets.speech_dataset_large import get_speech_dataset, window_class

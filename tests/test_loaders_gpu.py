@@ -76,7 +76,7 @@ def test_model_factory_from_checkpoint_files_reproduces_the_reference_run(tmp_pa
     enc, llm, lora, proj = rf.cfgs(fix)
     mc, kwargs = _write_assets(str(tmp_path), fix, om, hf_whisper, peft_dir)
     # with a peft directory the adapter shape comes from adapter_config.json, not from train_config.peft_config (slam_model.py:210-213)
-    tc = dict(enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=not peft_dir, seed=42,
+    tc = dict(model_name="asr", enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=not peft_dir, seed=42,
               peft_config=dict(peft_method="lora", r=lora.r, lora_alpha=lora.alpha, target_modules=list(lora.targets), bias="none", task_type="CAUSAL_LM",
                                lora_dropout=0.0, inference_mode=False))
     model, tok = model_factory(OmegaConf.create(tc), OmegaConf.create(mc), metric="acc", **kwargs)
@@ -125,7 +125,7 @@ def test_missing_llm_weights_fail_loudly_on_the_gpu_box(tmp_path, monkeypatch):
     from slam_llm.models.slam_model import model_factory
     monkeypatch.delenv("SLAM_B200_RANDOM_INIT", raising=False)
     llm_dir = make_llm_dir(str(tmp_path / "llm"))
-    tc = OmegaConf.create(dict(enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=False, seed=42))
+    tc = OmegaConf.create(dict(model_name="asr", enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=False, seed=42))
     mc = OmegaConf.create(dict(llm_name="x", llm_path=llm_dir, llm_dim=256, encoder_name="whisper", encoder_path="tiny", encoder_dim=384,
                                encoder_projector="linear", encoder_projector_ds_rate=5))
     with pytest.raises(FileNotFoundError):

@@ -144,8 +144,9 @@ def test_lora_dropout_matches_oracle_given_the_same_masks():
 
 
 def test_deferred_update_is_the_same_arithmetic():
-    """defer_update: optimizer_step() records, the next forward applies it after the frozen front end; parameters after K steps are
-    bit-identical to the immediate mode, and every reader of the trainables (trainable_state) sees the update."""
+    """defer_update: optimizer_step() records, the next forward applies it after the frozen front end; losses and parameters after K steps
+    equal the immediate mode up to the reordering of fp32 atomics (CE sum, split-K / LoRA wgrad reductions), and every reader of the
+    trainables (trainable_state) sees the update."""
     c = CASES["tiny_dh64"]
     _, a = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
     _, b = build_pair(c["enc"], c["llm"], c["lora"], c["proj"])
@@ -154,12 +155,12 @@ def test_deferred_update_is_the_same_arithmetic():
     for _ in range(3):
         la, _ = a.train_step(batch, lr=1e-3, weight_decay=0.01)
         lb, _ = b.train_step(batch, lr=1e-3, weight_decay=0.01)
-        assert la.item() == lb.item()
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item())
     assert b._pending_update is not None                     # third update still pending ...
     sb = b.trainable_state()                                 # ... until somebody reads the trainables
     assert b._pending_update is None
     for k, v in a.trainable_state().items():
-        assert torch.equal(v, sb[k]), k
+        assert rel_l2(sb[k], v) < 1e-4, (k, rel_l2(sb[k], v))
 
 
 def test_cuda_graph_replay_is_the_same_arithmetic():
