@@ -624,6 +624,7 @@ class SlamStepB200:
         self.defer_update = False
         self._pending_update = None        # (lr, weight_decay, grad_div)
         self._pending_work = None          # torch.distributed Work of the in-flight gradient all-reduce
+        self._carry = None                 # gradients of earlier micro-steps (accumulation) while a backward is in progress
 
     # ------------------------------------------------------------------ state dict in the reference's key names
     def trainable_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
@@ -688,16 +689,33 @@ class SlamStepB200:
         key_mask = batch["attention_mask"].to(dev).to(torch.uint8).contiguous()
         mod_mask = batch["modality_mask"].to(dev).to(torch.uint8).contiguous()
         B, S = ids.shape
+        self.begin_decoder_pass(train)
+        aud = self.projector.forward(enc_out, save=train)
+        x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
+        out = self.decoder_loss(x, key_mask, labels, rows=batch.get("_rows"), targets=batch.get("_targets"), train=train, full_logits=full_logits)
+        if train:
+            self._ctx.update(mod_mask=mod_mask, Ta=aud.shape[1])
+        return out
+
+    def begin_decoder_pass(self, train: bool) -> None:
+        """Once per forward, before anything reads the trainables: land a deferred update, re-pack the adapters, arm LoRA dropout."""
+        self.flush_update()
         self.llm.pack_lora()                                                               # adapters change every optimizer step
         self.llm.dropout_active = bool(train and self.lora_dropout_enabled and self.llm.dropout_p > 0.0)
         self.llm.dropout_step += 1
-        aud = self.projector.forward(enc_out, save=train)
-        x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
+
+    def decoder_loss(self, x: torch.Tensor, key_mask: torch.Tensor, labels: torch.Tensor, rows=None, targets=None, train: bool = True,
+                     full_logits: bool = False):
+        """inputs_embeds bf16 [B,S,D] + key mask u8 [B,S] + labels -> (loss, acc, logits | None): the call `self.llm(inputs_embeds=...,
+        attention_mask=..., labels=...)` of slam_model.py:400 incl. the accuracy of :402-405.  Recipes that build inputs_embeds themselves
+        enter here (slam_model.llm_forward); decoder_backward() returns the gradient w.r.t. x."""
+        dev = self.device
+        B, S, _ = x.shape
         xf = self.llm.forward(x, key_mask, save=train)
-        if "_rows" in batch and not full_logits:
-            rows, tgts = batch["_rows"].to(dev), batch["_targets"].to(dev)
+        if rows is not None and not full_logits:
+            rows, tgts = rows.to(dev), targets.to(dev)
         else:
-            rows, tgts = self.label_rows(labels, full=full_logits)
+            rows, tgts = self.label_rows(labels.to(dev), full=full_logits)
         R = rows.numel()
         hsel = xf if full_logits else ops.gather_rows(xf, rows)
         logits = ops.gemm(hsel, self.llm.lm_head, out_f32=True)                            # fp32 logits (HF .float())
@@ -709,18 +727,36 @@ class SlamStepB200:
         loss = (loss_sum / nv).squeeze(0)
         acc = (n_correct.to(F32) / nv).squeeze(0)
         if train:
-            self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, mod_mask=mod_mask, Ta=aud.shape[1], R=R)
+            self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, R=R)
         return loss, acc, (logits.view(B, S, -1) if full_logits else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         """Backward of the last forward(train=True); grad_out is d(total)/d(loss) (device scalar, default 1)."""
+        mod_mask, ta = self._ctx["mod_mask"], self._ctx["Ta"]
+        self.backward_begin()
+        dx = self.decoder_backward(grad_out)
+        daud = ops.embed_merge_bwd(mod_mask, dx.contiguous(), ta)
+        self.projector.backward(daud)
+        self.backward_end()
+
+    def backward_begin(self) -> None:
+        self.flush_update()                                                               # never overwrite gradients an update still needs
+        self._carry = self.arena.grad.clone() if self.micro_steps > 0 else None           # gradient accumulation: kernels overwrite
+        self.arena.grad.zero_()                                                           # one memset: the LoRA wgrad products accumulate
+
+    def backward_end(self) -> None:
+        if self._carry is not None:
+            self.arena.grad.add_(self._carry)
+            self._carry = None
+        self.micro_steps += 1
+
+    def decoder_backward(self, grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """CE + lm_head + decoder backward of the last decoder_loss(train=True): LoRA gradients into the arena, returns d loss / d inputs_embeds
+        bf16 [B,S,D] (call between backward_begin() and backward_end())."""
         c = self._ctx
         self._ctx = None
         dev = self.device
-        self.flush_update()                                                               # never overwrite gradients an update still needs
-        carry = self.arena.grad.clone() if self.micro_steps > 0 else None                 # gradient accumulation: kernels overwrite
-        self.arena.grad.zero_()                                                           # one memset: the LoRA wgrad products accumulate
         gs = (1.0 / c["nv"]) if grad_out is None else (grad_out.to(dev, F32).reshape(1) / c["nv"])
         gs = gs.contiguous()
         logits = c["logits"]
@@ -735,12 +771,7 @@ class SlamStepB200:
         else:
             dxf = torch.zeros((M, self.llm_cfg.d), device=dev, dtype=BF16)
             ops.scatter_rows(dh, c["rows"], dxf)
-        dx = self.llm.backward(dxf)
-        daud = ops.embed_merge_bwd(c["mod_mask"], dx.contiguous(), c["Ta"])
-        self.projector.backward(daud)
-        if carry is not None:
-            self.arena.grad.add_(carry)
-        self.micro_steps += 1
+        return self.llm.backward(dxf)
 
     def allreduce_grads(self, async_op: bool = False):
         """The one data-path collective (DDP's bucket all-reduce, pipeline/finetune.py:181-184): SUM over ranks of the flat

@@ -18,10 +18,30 @@ def _bind(module, engine_projector, arena, names) -> None:
     module._b200 = engine_projector
 
 
+class _ProjectorFn(torch.autograd.Function):
+    """The projector as an autograd node, for recipes that call `self.encoder_projector(encoder_outs)` themselves and feed the result to
+    `self.llm(inputs_embeds=...)`: backward writes the weight / bias gradients into the flat arena (the encoder is frozen: no dX)."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, module):
+        ctx.module = module
+        return module._b200.forward(x.to(torch.bfloat16).contiguous(), save=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ctx.module._b200.backward(dy.to(torch.bfloat16).contiguous())
+        return None, None, None
+
+
 def _forward(module, x):
     if module._b200 is None:
         raise RuntimeError(f"{type(module).__name__} is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
-    return module._b200.forward(x.to(torch.bfloat16).contiguous(), save=torch.is_grad_enabled())
+    step = getattr(module, "_step", None)
+    if step is not None:
+        step.flush_update()                                      # a deferred optimizer step must land before the weights are read
+    if torch.is_grad_enabled():
+        return _ProjectorFn.apply(module._b200.arena.param, x, module)
+    return module._b200.forward(x.to(torch.bfloat16).contiguous(), save=False)
 
 
 class EncoderProjectorConcat(nn.Module):

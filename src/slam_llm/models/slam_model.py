@@ -300,6 +300,31 @@ class _StepLoss(torch.autograd.Function):
         return None, None, None
 
 
+class _LlmLoss(torch.autograd.Function):
+    """Decoder + lm_head + CE as ONE autograd node over inputs_embeds (see slam_model.llm_forward)."""
+
+    @staticmethod
+    def forward(ctx, inputs_embeds, owner, key_mask, labels, full):
+        eng = owner.b200
+        eng.begin_decoder_pass(True)
+        x = inputs_embeds.detach().to(eng.device, torch.bfloat16).contiguous()
+        loss, acc, logits = eng.decoder_loss(x, key_mask, labels, train=True, full_logits=full)
+        ctx.owner, ctx.in_dtype = owner, inputs_embeds.dtype
+        if logits is None:
+            logits = torch.empty(0, device=eng.device)
+        ctx.mark_non_differentiable(logits)
+        return loss.clone(), logits
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits):
+        owner = ctx.owner
+        eng = owner.b200
+        eng.backward_begin()
+        dx = eng.decoder_backward(grad_loss)
+        torch.autograd.Variable._execution_engine.queue_callback(owner._finish_split_backward)
+        return dx.to(ctx.in_dtype), None, None, None, None
+
+
 class _Outputs(types.SimpleNamespace):
     pass
 
@@ -339,6 +364,7 @@ class slam_model(nn.Module):
                 mine[k].copy_(v.to(device, torch.float32))
         self.b200 = SlamStepB200.from_parts(encoder.b200, eng_proj, llm.b200, arena, device)
         object.__setattr__(llm, "_step", self)       # plain attribute: registering the parent as a sub-module would create a cycle
+        object.__setattr__(encoder_projector, "_step", self.b200)
         arena.param.requires_grad_(True)
         self._grad_views_set = False
         self.ddp_world_size = 1
@@ -379,9 +405,39 @@ class slam_model(nn.Module):
             self.b200.allreduce_grads(async_op=self.b200.defer_update)
         self._bind_grad_views()
 
-    # ---- decoder entry used by recipes that override forward() and call self.llm(...) themselves
+    # ---- decoder entry used by recipes that override forward() and call self.llm(...) themselves (slam_model.py:400)
     def llm_forward(self, inputs_embeds, attention_mask, labels):
-        raise NotImplementedError("calling self.llm(inputs_embeds=...) directly is not wired yet; use slam_model.forward")
+        """`self.llm(inputs_embeds=..., attention_mask=..., labels=...)` -> object with .loss / .logits, autograd-connected to inputs_embeds:
+        `loss.backward()` runs the B200 decoder backward (LoRA gradients into the arena) and hands d loss / d inputs_embeds to whatever torch
+        graph produced the embeddings (typically the projector module, itself an autograd node over the arena).  Without labels: eval logits."""
+        eng = self.b200
+        if inputs_embeds is None:
+            raise NotImplementedError("the B200 decoder is driven by inputs_embeds (as slam_model.forward does); input_ids-only calls are not implemented")
+        dev = eng.device
+        B, S = inputs_embeds.shape[:2]
+        key_mask = (torch.ones(B, S, dtype=torch.uint8, device=dev) if attention_mask is None else attention_mask.to(dev).to(torch.uint8).contiguous())
+        train = torch.is_grad_enabled() and labels is not None
+        eng.lora_dropout_enabled = self.training
+        if labels is None:
+            eng.begin_decoder_pass(False)
+            x = inputs_embeds.detach().to(dev, torch.bfloat16).contiguous()
+            dummy = torch.full((B, S), -100, dtype=torch.int64, device=dev)
+            _, _, logits = eng.decoder_loss(x, key_mask, dummy, train=False, full_logits=True)
+            return _Outputs(loss=None, logits=logits)
+        full = (not train) or bool(self.train_config.get("b200_full_logits", False))
+        if not train:
+            eng.begin_decoder_pass(False)
+            loss, acc, logits = eng.decoder_loss(inputs_embeds.detach().to(dev, torch.bfloat16).contiguous(), key_mask, labels, train=False, full_logits=full)
+            return _Outputs(loss=loss, logits=logits)
+        loss, logits = _LlmLoss.apply(inputs_embeds, self, key_mask, labels, full)
+        return _Outputs(loss=loss, logits=logits)
+
+    def _finish_split_backward(self):
+        """Runs once the autograd pass that contained _LlmLoss.backward has finished (projector node included)."""
+        self.b200.backward_end()
+        if self.ddp_world_size > 1 and self.ddp_sync:
+            self.b200.allreduce_grads(async_op=self.b200.defer_update)
+        self._bind_grad_views()
 
     # ---- forward (slam_model.py:283-407)
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None, labels=None,

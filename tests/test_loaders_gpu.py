@@ -118,6 +118,63 @@ def test_model_factory_from_checkpoint_files_reproduces_the_reference_run(tmp_pa
         assert rf.rel_max(h[:, :40], fix["encoder_out"]) < 2e-2
 
 
+def test_recipe_that_overrides_forward_and_calls_the_llm_itself(tmp_path):
+    """Recipes such as examples/st_covost2/model/slam_model_st.py override forward(): they call the encoder, the projector, the embedding and
+    `self.llm(inputs_embeds=..., attention_mask=..., labels=...)` themselves (slam_model.py:356-400 written out in the recipe).  That path
+    runs through autograd nodes (projector, decoder+CE) over the same kernels; loss and gradients must equal the reference run's."""
+    import slam_llm  # noqa: F401
+    from omegaconf import OmegaConf
+    from slam_llm.models.slam_model import model_factory
+    fix = rf.load("ref_tiny.pt")
+    om = rf.oracle_model(fix)
+    enc, llm, lora, proj = rf.cfgs(fix)
+    mc, kwargs = _write_assets(str(tmp_path), fix, om, False, False)
+    tc = dict(model_name="asr", enable_fsdp=False, enable_ddp=False, quantization=False, freeze_llm=True, freeze_encoder=True, use_peft=True, seed=42,
+              peft_config=dict(peft_method="lora", r=lora.r, lora_alpha=lora.alpha, target_modules=list(lora.targets), bias="none", task_type="CAUSAL_LM",
+                               lora_dropout=0.0, inference_mode=False))
+    model, _ = model_factory(OmegaConf.create(tc), OmegaConf.create(mc), metric="acc", **kwargs)
+    model.train()
+    batch = {k: v.cuda() for k, v in rf.batch_of(fix).items()}
+    mel = model.b200.log_mel(batch["audio_pcm"])
+    # --- the body of the reference's slam_model.forward, executed by "the recipe"
+    encoder_outs = model.encoder.extract_variable_length_features(mel.permute(0, 2, 1))
+    encoder_outs = model.encoder_projector(encoder_outs)
+    input_ids = batch["input_ids"].clone()
+    input_ids[input_ids == -1] = 0
+    inputs_embeds = model.llm.model.model.embed_tokens(input_ids) if not hasattr(model.llm.model, "embed_tokens") else model.llm.model.embed_tokens(input_ids)
+    modality_mask = batch["modality_mask"]
+    start = (modality_mask == True).float().argmax(dim=1)  # noqa: E712
+    lengths = torch.clamp(modality_mask.sum(dim=1), max=encoder_outs.shape[1]).tolist()
+    pad = torch.zeros_like(inputs_embeds)
+    for i in range(encoder_outs.shape[0]):
+        pad[i, start[i]:start[i] + lengths[i]] = encoder_outs[i][:lengths[i]]
+    inputs_embeds = pad + inputs_embeds * (~modality_mask[:, :, None])
+    outputs = model.llm(inputs_embeds=inputs_embeds, attention_mask=batch["attention_mask"], labels=batch["labels"])
+    assert abs(outputs.loss.item() - fix["loss"]) <= 5e-3 * abs(fix["loss"]), (outputs.loss.item(), fix["loss"])
+    outputs.loss.backward()
+    named = dict(model.named_parameters())
+    gmax = max((g["norm"] if rf.is_probe(g) else g.norm().item()) for g in fix["grads"].values())
+    checked = 0
+    for k, g_ref in fix["grads"].items():
+        g = named[k].grad
+        assert g is not None, k
+        if rf.is_probe(g_ref):
+            if g_ref["norm"] >= 1e-3 * gmax:
+                rf.check_probe(g, g_ref, norm_rel=3e-2, head_cos=0.99, what=k)
+                checked += 1
+        elif g_ref.norm().item() >= 1e-3 * gmax:
+            assert rf.cosine(g, g_ref) > 0.99 and rf.rel_l2(g, g_ref) < 3e-2, (k, rf.cosine(g, g_ref), rf.rel_l2(g, g_ref))
+            checked += 1
+    assert checked >= 6
+    # logits-only call (no labels), as decode-side recipe code does
+    with torch.no_grad():
+        lo = model.llm(inputs_embeds=inputs_embeds.detach(), attention_mask=batch["attention_mask"])
+    assert lo.loss is None and lo.logits.shape[:2] == batch["input_ids"].shape
+    rows = rf.label_rows(batch["labels"].cpu())
+    lab = lo.logits.float().cpu()[:, :-1][rows]
+    assert rf.rel_max(lab, fix["label_logits"]) < 2e-2
+
+
 def test_missing_llm_weights_fail_loudly_on_the_gpu_box(tmp_path, monkeypatch):
     import slam_llm  # noqa: F401
     from omegaconf import OmegaConf
