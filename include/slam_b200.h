@@ -140,6 +140,9 @@ typedef struct slam_attn_args {
   float* dq_accum;               /* f32 scratch [B,Sq,Hq,dh]: dQ partial sums (zeroed by the call) */
   void* dkv_part;                /* optional bf16 scratch [2,B,Sk,Hq,dh] (GQA only): per-Q-head dK/dV partials, summed over each
                                     KV group by a follow-up kernel -> Hq/Hkv times more CTAs; NULL = loop over the group in one CTA */
+  const float* rope_cos;         /* optional f32 [>= max(sq, sk), dh/2] (both or neither): q and k were rotated by HF apply_rotary_pos_emb with */
+  const float* rope_sin;         /* position = token index; the backward's finishing kernel then returns dQ / dK w.r.t. the UN-rotated q / k
+                                    (inverse rotation fused with the GQA group sum and the fp32 -> bf16 conversion of dQ) */
 } slam_attn_args;
 int slam_attn_fwd(const slam_attn_args* a, void* stream);
 int slam_attn_bwd(const slam_attn_args* a, void* stream);

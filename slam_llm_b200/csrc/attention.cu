@@ -52,6 +52,8 @@ struct AttnP {
   float* delta;
   float* dq_accum;
   bf16* dkv_part;   // optional [2][B][Sk][Hq][dh]: per-q-head dK/dV partials (GQA): 4x more CTAs, group-summed afterwards
+  const float* rope_cos;   // optional f32 [seq, dh/2]: the backward's finishing kernel applies the INVERSE rotation to dQ / dK
+  const float* rope_sin;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -549,6 +551,89 @@ __global__ void attn_group_sum_kernel(const bf16* __restrict__ part, bf16* __res
   }
 }
 
+// Finishing pass of the attention backward in ONE kernel (was: group sum, fp32 -> bf16 conversion of dQ and a separate inverse-RoPE pass):
+//   dQ  = [R^T] dq_accum                       f32 [rows_q, Hq, dh] -> bf16 (row stride lddq)
+//   dK  = [R^T] sum over the KV group of dK partials (or dK itself when the kernel wrote it directly)
+//   dV  =       sum over the KV group of dV partials (nothing to do when written directly)
+// R^T = inverse rotate-half RoPE with position = row % seq (HF apply_rotary_pos_emb transposed), applied when cos/sin are given.
+// One thread = 8 "lo" + 8 "hi" elements (d, d + dh/2) of one (row, head).
+__global__ void attn_bwd_finish_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq, long long rows_q, int seq_q, int hq,
+                                       const bf16* __restrict__ part, bf16* __restrict__ dk, long long lddk, bf16* __restrict__ dv, long long lddv,
+                                       long long rows_k, int seq_k, int hkv, int dh, const float* __restrict__ cosT, const float* __restrict__ sinT) {
+  pdl_trigger();
+  pdl_wait();
+  const int half = dh / 2;
+  const int vph = half / 8;                                           // threads per (row, head)
+  const int g = hq / hkv;
+  const long long nq = rows_q * hq * vph;
+  const long long nk = rows_k * hkv * vph;
+  const bool k_work = part != nullptr || cosT != nullptr;           // dK needs a pass (group sum and / or rotation)
+  const bool v_work = part != nullptr;
+  const long long total = nq + (k_work ? nk : 0) + (v_work ? nk : 0);
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    float lo[8], hi[8];
+    bf16* dst;
+    int pos;
+    bool rotate = cosT != nullptr;
+    int v;
+    if (i < nq) {
+      v = static_cast<int>(i % vph);
+      const int h = static_cast<int>((i / vph) % hq);
+      const long long r = i / (static_cast<long long>(vph) * hq);
+      const float* src = acc + (r * hq + h) * dh + v * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(src + half), b1 = *reinterpret_cast<const float4*>(src + half + 4);
+      lo[0] = a0.x; lo[1] = a0.y; lo[2] = a0.z; lo[3] = a0.w; lo[4] = a1.x; lo[5] = a1.y; lo[6] = a1.z; lo[7] = a1.w;
+      hi[0] = b0.x; hi[1] = b0.y; hi[2] = b0.z; hi[3] = b0.w; hi[4] = b1.x; hi[5] = b1.y; hi[6] = b1.z; hi[7] = b1.w;
+      dst = dq + r * lddq + static_cast<long long>(h) * dh + v * 8;
+      pos = static_cast<int>(r % seq_q);
+    } else {
+      long long j = i - nq;
+      const bool is_v = k_work ? j >= nk : true;
+      if (is_v && k_work) j -= nk;
+      v = static_cast<int>(j % vph);
+      const int hk = static_cast<int>((j / vph) % hkv);
+      const long long r = j / (static_cast<long long>(vph) * hkv);
+      bf16* out = (is_v ? dv + r * lddv : dk + r * lddk) + static_cast<long long>(hk) * dh + v * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) lo[e] = hi[e] = 0.f;
+      if (part != nullptr) {
+        const bf16* src = part + ((is_v ? rows_k : 0) + r) * hq * dh + static_cast<long long>(hk) * g * dh + v * 8;
+        for (int t = 0; t < g; ++t) {
+          float a[8], b[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(src + static_cast<long long>(t) * dh), a);
+          unpack8(*reinterpret_cast<const bf16x8*>(src + static_cast<long long>(t) * dh + half), b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            lo[e] += a[e];
+            hi[e] += b[e];
+          }
+        }
+      } else {
+        unpack8(*reinterpret_cast<const bf16x8*>(out), lo);
+        unpack8(*reinterpret_cast<const bf16x8*>(out + half), hi);
+      }
+      dst = out;
+      pos = static_cast<int>(r % seq_k);
+      rotate = rotate && !is_v;
+    }
+    if (rotate) {
+      const float* c = cosT + static_cast<long long>(pos) * half + v * 8;
+      const float* sn = sinT + static_cast<long long>(pos) * half + v * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float l = lo[e], h2 = hi[e];
+        lo[e] = l * c[e] + h2 * sn[e];
+        hi[e] = h2 * c[e] - l * sn[e];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dst) = pack8(lo);
+    *reinterpret_cast<bf16x8*>(dst + half) = pack8(hi);
+  }
+}
+
 // dq_accum f32 [B,Sq,Hq,DH] -> dq bf16 with row stride lddq
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq, long long rows, int width) {
   pdl_trigger();
@@ -590,6 +675,8 @@ static int fill_params(const slam_attn_args* a, AttnP& p, bool bwd) {
   p.delta = a->delta;
   p.dq_accum = a->dq_accum;
   p.dkv_part = (bwd && a->hq != a->hkv) ? reinterpret_cast<bf16*>(a->dkv_part) : nullptr;
+  p.rope_cos = bwd ? a->rope_cos : nullptr;
+  p.rope_sin = bwd ? a->rope_sin : nullptr;
   if (bwd) {
     SLAM_CHECK_ARG(a->lse && a->delta && a->dq_accum && a->dout && a->dq && a->dk && a->dv, "attn_bwd: missing buffers");
     SLAM_CHECK_ARG(a->lddo % 8 == 0 && a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0, "attn_bwd: row strides must be multiples of 8");
@@ -677,18 +764,18 @@ extern "C" int slam_attn_bwd(const slam_attn_args* a, void* stream) {
   rc = use_tc ? fmha_bwd_tc_try(a, st) : 1;           // tcgen05 / TMEM kernel for the Llama decoder shape (dh = 128)
   if (rc == 1) rc = a->dh == 64 ? launch_bwd<64, 64>(p, st) : launch_bwd<128, 32>(p, st);
   if (rc != 0) return rc;
-  if (p.dkv_part != nullptr) {
-    const long long krows = static_cast<long long>(p.batch) * p.sk;
-    long long gb = ceil_div(2 * krows * (p.hkv * a->dh / 8), 256);
-    if (gb > num_sms() * 16) gb = num_sms() * 16;
-    launch_pdl(attn_group_sum_kernel, static_cast<unsigned>(gb), 256, 0, st, p.dkv_part, p.dk, p.lddk, p.dv, p.lddv, krows, p.hq, p.hkv, a->dh);
-    SLAM_LAUNCH_CHECK("slam_attn_bwd.group_sum");
-  }
   SLAM_CHECK_ARG(p.lddq >= width || p.hq * a->dh <= p.lddq, "attn_bwd: lddq too small");
-  const long long nvec = rows * (width / 4);
-  long long blocks = ceil_div(nvec, 256);
-  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  launch_pdl(attn_dq_convert_kernel, static_cast<unsigned>(blocks), 256, 0, st, p.dq_accum, p.dq, p.lddq, rows, width);
-  SLAM_LAUNCH_CHECK("slam_attn_bwd.convert");
+  SLAM_CHECK_ARG((a->rope_cos == nullptr) == (a->rope_sin == nullptr), "attn_bwd: rope_cos and rope_sin go together");
+  SLAM_CHECK_ARG(a->dh % 16 == 0, "attn_bwd: dh %% 16 != 0");
+  {
+    const long long krows = static_cast<long long>(p.batch) * p.sk;
+    const int vph = a->dh / 16;
+    long long items = rows * p.hq * vph + 2 * krows * p.hkv * vph;
+    long long blocks = ceil_div(items, 256);
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    launch_pdl(attn_bwd_finish_kernel, static_cast<unsigned>(blocks), 256, 0, st, p.dq_accum, p.dq, p.lddq, rows, p.sq, p.hq,
+               static_cast<const bf16*>(p.dkv_part), p.dk, p.lddk, p.dv, p.lddv, krows, p.sk, p.hkv, a->dh, p.rope_cos, p.rope_sin);
+    SLAM_LAUNCH_CHECK("slam_attn_bwd.finish");
+  }
   return 0;
 }

@@ -318,5 +318,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// eight bf16 values as one 16-byte vector
+struct alignas(16) bf16x8 {
+  uint32_t w[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = unpack_bf16x2(p.w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
 
 }  // namespace slam

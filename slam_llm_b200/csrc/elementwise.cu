@@ -6,24 +6,6 @@
 
 namespace slam {
 
-struct alignas(16) bf16x8 {
-  uint32_t w[4];
-};
-__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = unpack_bf16x2(p.w[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
-  bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-  return p;
-}
-
 // block-wide sum of one float (blockDim.x <= 1024, multiple of 32)
 __device__ __forceinline__ float block_sum(float v, float* sbuf) {
   v = warp_sum(v);

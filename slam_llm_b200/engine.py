@@ -575,8 +575,8 @@ class LlamaLoRAB200:
             v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
             dqkv = torch.empty_like(qkv)
             ops.attn_bwd(q, k, v, kp["attn"], kp["lse"], dattn.view(B, S, H, dh), causal=True, scale=scale, key_mask=sv["key_mask"],
-                         dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh))
-            ops.rope_(dqkv[:, : Dq + Dkv], H + Hkv, dh, S, cos, sin, inverse=True)
+                         dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh),
+                         rope=(cos, sin))                                               # inverse RoPE of dQ / dK fused into the finishing kernel
             dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp["sv_qkv"])
             dx = ops.rmsnorm_bwd(dxn1, kp["x"], Lw["ln1"], kp["rstd1"], dres=dx2)
             sv["layers"][li] = None

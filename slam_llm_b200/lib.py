@@ -56,6 +56,8 @@ class AttnArgs(C.Structure):
         ("delta", _vp),
         ("dq_accum", _vp),
         ("dkv_part", _vp),
+        ("rope_cos", _vp),
+        ("rope_sin", _vp),
     ]
 
 

@@ -237,7 +237,9 @@ def attn_fwd(q, k, v, *, causal: bool, scale: float, key_mask=None, out=None, ne
     return out, lse
 
 
-def attn_bwd(q, k, v, out, lse, dout, *, causal: bool, scale: float, key_mask=None, dq=None, dk=None, dv=None):
+def attn_bwd(q, k, v, out, lse, dout, *, causal: bool, scale: float, key_mask=None, dq=None, dk=None, dv=None, rope=None):
+    """rope = (cos, sin) f32 [S, dh/2]: q / k are the ROTATED projections; dq / dk come back w.r.t. the un-rotated ones (inverse RoPE fused
+    into the finishing kernel together with the GQA group sum and the dQ fp32 -> bf16 conversion)."""
     B, Sq, Hq, dh = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
     if dq is None:
@@ -259,6 +261,13 @@ def attn_bwd(q, k, v, out, lse, dout, *, causal: bool, scale: float, key_mask=No
     a.delta, a.dq_accum = delta.data_ptr(), dq_accum.data_ptr()
     dkv_part = torch.empty((2, B, Sk, Hq, dh), device=q.device, dtype=BF16) if Hq != Hkv else None   # GQA: split CTAs per Q head
     a.dkv_part = _p(dkv_part)
+    if rope is not None:
+        cos, sin = rope
+        _req(cos, F32, "attn_bwd.rope_cos"); _req(sin, F32, "attn_bwd.rope_sin")
+        assert cos.is_contiguous() and sin.is_contiguous() and cos.shape[0] >= max(Sq, Sk) and cos.shape[1] == dh // 2 and sin.shape == cos.shape
+        a.rope_cos, a.rope_sin = cos.data_ptr(), sin.data_ptr()
+    else:
+        a.rope_cos = a.rope_sin = None
     _l.check(_l.load().slam_attn_bwd(C.byref(a), _stream()), "slam_attn_bwd")
     return dq, dk, dv
 

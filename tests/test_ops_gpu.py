@@ -337,6 +337,19 @@ def test_attention_fwd_bwd(ops, B, S, Hq, Hkv, dh, causal, masked):
     for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
         assert rel_err(got, want) < 3e-2, (name, rel_err(got, want))
         assert cos_sim(got, want) > 0.999, (name, cos_sim(got, want))
+    # rope=(cos, sin): the finishing kernel also applies the inverse rotation to dQ / dK (gradients w.r.t. the un-rotated projections)
+    cos, sin = _rope_tables(S, dh, 500000.0)
+    dq2, dk2, dv2 = ops.attn_bwd(q, k, v, out, lse, dout, causal=causal, scale=scale, key_mask=key_mask, rope=(cos, sin))
+
+    def unrotate(g):
+        c = torch.cat([cos, cos], -1)[None, :, None, :]
+        s_ = torch.cat([sin, sin], -1)[None, :, None, :]
+        g = g.float()
+        rot = torch.cat([g[..., dh // 2:], -g[..., :dh // 2]], -1)          # R^T g = g cos - rotate_half(g) sin
+        return g * c + rot * s_
+    assert rel_err(dq2, unrotate(qr.grad)) < 3e-2 and cos_sim(dq2, unrotate(qr.grad)) > 0.999
+    assert rel_err(dk2, unrotate(kr.grad)) < 3e-2 and cos_sim(dk2, unrotate(kr.grad)) > 0.999
+    assert rel_err(dv2, vr.grad) < 3e-2
 
 
 @pytest.mark.parametrize("B,S,H", [(2, 1500, 6), (1, 333, 20), (4, 1500, 20), (3, 128, 2), (1, 129, 1), (2, 1000, 8)])
