@@ -18,6 +18,7 @@ constexpr int NFFT = 400;
 constexpr int HOP = 160;
 constexpr int NBIN = 201;
 constexpr int FR = 8;  // frames per CTA
+static_assert(FR == 8, "the DFT loop reads the 8 frames of a sample as two float4");
 
 __device__ __forceinline__ int float_key(float f) {
   const int i = __float_as_int(f);
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
   pdl_wait();
   __shared__ float s_cos[NFFT];
   __shared__ float s_sin[NFFT];
-  __shared__ float s_x[FR][NFFT];      // windowed frames
+  __shared__ __align__(16) float s_x[NFFT][FR];      // windowed frames, sample-major: the FR frames of one sample are two 16-byte broadcast loads
   __shared__ float s_pow[FR][NBIN + 3];
   __shared__ float s_red[8];
   const int b = blockIdx.y;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
       const float hann = 0.5f - 0.5f * s_cos[n];  // periodic hann window (torch.hann_window(400))
       v = w[j] * hann;
     }
-    s_x[f][n] = v;
+    s_x[n][f] = v;
   }
   __syncthreads();
 
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
     int idx = 0;
     for (int n = 0; n < NFFT; ++n) {
       const float c = s_cos[idx], s = s_sin[idx];
+      const float4 x0 = *reinterpret_cast<const float4*>(&s_x[n][0]), x1 = *reinterpret_cast<const float4*>(&s_x[n][4]);
+      const float xv[FR] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int f = 0; f < FR; ++f) {
-        const float xv = s_x[f][n];
-        re[f] = fmaf(xv, c, re[f]);
-        im[f] = fmaf(xv, s, im[f]);
+        re[f] = fmaf(xv[f], c, re[f]);
+        im[f] = fmaf(xv[f], s, im[f]);
       }
       idx += k;
       if (idx >= NFFT) idx -= NFFT;
