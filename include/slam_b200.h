@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SLAM_B200_ABI_VERSION 4
+#define SLAM_B200_ABI_VERSION 5
 
 int slam_abi_version(void);
 const char* slam_last_error(void);

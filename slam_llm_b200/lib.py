@@ -124,8 +124,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.slam_abi_version() != 4:
-        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 4")
+    if lib.slam_abi_version() != 5:
+        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 5")
     _lib = lib
     return lib
 
