@@ -159,6 +159,15 @@ int slam_embed_merge(const int64_t* ids, const uint8_t* modality_mask, const voi
 int slam_embed_merge_bwd(const uint8_t* modality_mask, const void* dx_bf16, void* daudio_bf16,
                          int32_t ta, int32_t batch, int32_t s, int32_t d, void* stream);
 
+/* full fine-tune (train_config.freeze_llm=false, models/slam_model.py:205-208 not taken; examples/s2s): gradients of the decoder's own
+ * parameters that are not GEMM products.
+ *   slam_rmsnorm_wgrad: dw[c] += sum_r dy[r,c] * x[r,c] * rstd[r]   (LlamaRMSNorm weight; dw f32 [d], ACCUMULATED: zero it first)
+ *   slam_embed_grad:    dE[max(ids[r],0)] += dx[r] for rows with modality_mask[r] == 0  (embedding rows used by the merge, slam_model.py:392;
+ *                       dE f32 [vocab, d], accumulated with atomics; rows = B*S) */
+int slam_rmsnorm_wgrad(const void* dy_bf16, const void* x_bf16, const float* rstd, int32_t rows, int32_t d, float* dw, void* stream);
+int slam_embed_grad(const int64_t* ids, const uint8_t* modality_mask, const void* dx_bf16, float* dE, int32_t rows, int32_t d,
+                    int32_t vocab, void* stream);
+
 /* a5  Llama decoder element-wise kernels (HF LlamaRMSNorm / apply_rotary_pos_emb / LlamaMLP). */
 int slam_rmsnorm_fwd(const void* x_bf16, const void* w_bf16, void* y_bf16, float* rstd, int32_t rows,
                      int32_t d, float eps, void* stream);

@@ -56,6 +56,8 @@ class LlmCfg:
     ffn: int = 5632
     rope_theta: float = 10000.0
     eps: float = 1e-5
+    qkv_bias: bool = False         # Qwen2: biases on q/k/v projections
+    tie_embeddings: bool = False   # Qwen2-0.5B: lm_head shares the embedding table
 
     @property
     def dh(self) -> int:
@@ -155,12 +157,15 @@ def init_llm(cfg: LlmCfg, seed: int = 43, std: float = 0.02) -> Dict[str, torch.
         p = f"model.layers.{i}."
         for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
             w[p + f"self_attn.{name}.weight"] = n(*linear_shape(cfg, name))
+            if cfg.qkv_bias and name != "o_proj":
+                w[p + f"self_attn.{name}.bias"] = n(linear_shape(cfg, name)[0]) * 5
         for name in ("gate_proj", "up_proj", "down_proj"):
             w[p + f"mlp.{name}.weight"] = n(*linear_shape(cfg, name))
         w[p + "input_layernorm.weight"] = 1.0 + n(cfg.d)
         w[p + "post_attention_layernorm.weight"] = 1.0 + n(cfg.d)
     w["model.norm.weight"] = 1.0 + n(cfg.d)
-    w["lm_head.weight"] = n(cfg.vocab, cfg.d)
+    if not cfg.tie_embeddings:
+        w["lm_head.weight"] = n(cfg.vocab, cfg.d)
     return w
 
 
@@ -367,10 +372,10 @@ def rotate_half(x: torch.Tensor) -> torch.Tensor:
 
 
 def lora_linear(x: torch.Tensor, weight: torch.Tensor, lw: Dict[str, torch.Tensor], prefix: str, lora: Optional[LoraCfg],
-                masks: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                masks: Optional[Dict[str, torch.Tensor]] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """peft 0.6 lora.Linear.forward: F.linear(x, W) + B(A(dropout(x))) * alpha/r.  Dropout is deterministic here: `masks`
     (prefix -> keep/(1-p) tensor shaped like x) stands in for nn.Dropout's random mask; None = dropout 0."""
-    y = F.linear(x, weight)
+    y = F.linear(x, weight, bias)
     a_key = prefix + "lora_A.default.weight"
     if lora is not None and a_key in lw:
         xd = x if masks is None or prefix not in masks else x * masks[prefix].view_as(x)
@@ -394,9 +399,9 @@ def llama_forward(w: Dict[str, torch.Tensor], lw: Dict[str, torch.Tensor], cfg: 
     for i in range(cfg.layers):
         p = f"model.layers.{i}."
         h = rms_norm(x, w[p + "input_layernorm.weight"], cfg.eps)
-        q = lora_linear(h, w[p + "self_attn.q_proj.weight"], lw, p + "self_attn.q_proj.", lora, lora_masks)
-        k = lora_linear(h, w[p + "self_attn.k_proj.weight"], lw, p + "self_attn.k_proj.", lora, lora_masks)
-        v = lora_linear(h, w[p + "self_attn.v_proj.weight"], lw, p + "self_attn.v_proj.", lora, lora_masks)
+        q = lora_linear(h, w[p + "self_attn.q_proj.weight"], lw, p + "self_attn.q_proj.", lora, lora_masks, w.get(p + "self_attn.q_proj.bias"))
+        k = lora_linear(h, w[p + "self_attn.k_proj.weight"], lw, p + "self_attn.k_proj.", lora, lora_masks, w.get(p + "self_attn.k_proj.bias"))
+        v = lora_linear(h, w[p + "self_attn.v_proj.weight"], lw, p + "self_attn.v_proj.", lora, lora_masks, w.get(p + "self_attn.v_proj.bias"))
         q = q.view(B, S, H, dh).transpose(1, 2)
         k = k.view(B, S, Hkv, dh).transpose(1, 2)
         v = v.view(B, S, Hkv, dh).transpose(1, 2)
@@ -415,7 +420,7 @@ def llama_forward(w: Dict[str, torch.Tensor], lw: Dict[str, torch.Tensor], cfg: 
         if return_hidden:
             hiddens.append(x)
     x = rms_norm(x, w["model.norm.weight"], cfg.eps)
-    logits = F.linear(x, w["lm_head.weight"]).float()
+    logits = F.linear(x, w.get("lm_head.weight", w["model.embed_tokens.weight"])).float()      # tied embeddings: lm_head IS the embedding table
     return (logits, hiddens) if return_hidden else logits
 
 
@@ -455,6 +460,7 @@ class OracleModel:
     lora_w: Dict[str, torch.Tensor]
     proj_w: Dict[str, torch.Tensor]
     adam_state: dict = field(default_factory=dict)
+    train_llm: bool = False        # freeze_llm=false (full fine-tune, examples/s2s): every decoder parameter is trainable
 
     @classmethod
     def build(cls, enc_cfg, llm_cfg, lora_cfg, proj_cfg, seed: int = 42):
@@ -471,6 +477,8 @@ class OracleModel:
         """Reference checkpoint key names (SURVEY.md §5 checkpoint row)."""
         out = {f"encoder_projector.{k}": v for k, v in self.proj_w.items()}
         out.update({f"llm.base_model.model.{k}": v for k, v in self.lora_w.items()})
+        if self.train_llm:
+            out.update({f"llm.{k}": v for k, v in self.llm_w.items()})                   # HF names under the `llm.` attribute (no peft wrapper)
         return out
 
     def forward(self, batch: Dict[str, torch.Tensor], return_all: bool = False, lora_masks=None):
@@ -479,7 +487,7 @@ class OracleModel:
         mel = batch.get("audio_mel")
         if mel is None:
             mel = batch_log_mel(batch["audio_pcm"], self.enc_cfg.n_mels, batch.get("audio_pcm_lengths"))
-        dtype = self.llm_w["lm_head.weight"].dtype
+        dtype = self.llm_w["model.embed_tokens.weight"].dtype
         mel = mel.to(dtype)
         with torch.no_grad():                                            # encoder frozen (slam_model.py:110-113)
             enc = whisper_encoder(self.enc_w, self.enc_cfg, mel)

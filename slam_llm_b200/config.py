@@ -25,6 +25,8 @@ class LlmCfg:
     ffn: int = 5632
     rope_theta: float = 10000.0
     eps: float = 1e-5
+    qkv_bias: bool = False         # Qwen2: biases on the q/k/v projections
+    tie_embeddings: bool = False   # lm_head shares the embedding table (Qwen2-0.5B)
 
     @property
     def dh(self) -> int:
@@ -71,6 +73,7 @@ LLM = {
     "tinyllama-1.1b": LlmCfg(32000, 2048, 22, 32, 4, 5632, 10000.0, 1e-5),
     "llama-3-8b": LlmCfg(128256, 4096, 32, 32, 8, 14336, 500000.0, 1e-5),
     "vicuna-7b": LlmCfg(32000, 4096, 32, 32, 32, 11008, 10000.0, 1e-5),
+    "qwen2-0.5b": LlmCfg(151936, 896, 24, 14, 2, 4864, 1000000.0, 1e-6, True, True),
 }
 
 ATTN_LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj")

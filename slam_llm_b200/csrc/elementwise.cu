@@ -171,6 +171,49 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, int rows,
     atomicAdd(out + c, s);
   }
 }
+// RMSNorm weight gradient (full fine-tune, freeze_llm=false): dw[c] += sum_r dy[r,c] * x[r,c] * rstd[r]   (y = w * x * rstd)
+__global__ void rmsnorm_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ rstd, int rows, int cols,
+                                     float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int rows_per = static_cast<int>(ceil_div(rows, gridDim.y));
+  const int r_begin = blockIdx.y * rows_per;
+  const int r_end = min(rows, r_begin + rows_per);
+  float acc = 0.0f;
+  if (c < cols)
+    for (int r = r_begin + ry; r < r_end; r += 8) {
+      const int64_t i = static_cast<int64_t>(r) * cols + c;
+      acc += __bfloat162float(dy[i]) * __bfloat162float(x[i]) * rstd[r];
+    }
+  part[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x & 31];
+    atomicAdd(out + c, s);
+  }
+}
+
+// Embedding-table gradient of the merge (full fine-tune): dE[max(ids[r], 0)] += dx[r] for every row whose modality mask is 0 — the rows
+// that took `embed[ids] * (~mask)` in slam_model.py:392.  fp32 atomics (token ids repeat); one block per row.
+__global__ void embed_grad_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, const bf16* __restrict__ dx, float* __restrict__ de,
+                                  int d, int vocab) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t r = blockIdx.x;
+  if (mask[r]) return;
+  int64_t id = ids[r];
+  if (id < 0) id = 0;
+  if (id >= vocab) return;
+  const bf16* src = dx + r * d;
+  float* dst = de + id * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) atomicAdd(dst + k, __bfloat162float(src[k]));
+}
+
 __global__ void zero_f32_kernel(float* p, int64_t n) {
   pdl_trigger();
   pdl_wait();
@@ -1048,6 +1091,21 @@ int slam_embed_merge(const int64_t* ids, const uint8_t* mask, const void* audio,
   dim3 grid(s, batch);
   launch_pdl(embed_merge_kernel, grid, 128, 0, ST(stream), ids, mask, CBF(audio), ta, CBF(embed), BF(x), s, d);
   SLAM_LAUNCH_CHECK("slam_embed_merge");
+  return 0;
+}
+int slam_rmsnorm_wgrad(const void* dy, const void* x, const float* rstd, int32_t rows, int32_t d, float* dw, void* stream) {
+  SLAM_CHECK_ARG(rows > 0 && d > 0, "rmsnorm_wgrad: bad shape");
+  int ysplit = static_cast<int>(ceil_div(rows, 256));
+  if (ysplit > 64) ysplit = 64;
+  dim3 grid(static_cast<unsigned>(ceil_div(d, 32)), static_cast<unsigned>(ysplit));
+  launch_pdl(rmsnorm_wgrad_kernel, grid, 256, 0, ST(stream), CBF(dy), CBF(x), rstd, rows, d, dw);
+  SLAM_LAUNCH_CHECK("slam_rmsnorm_wgrad");
+  return 0;
+}
+int slam_embed_grad(const int64_t* ids, const uint8_t* mask, const void* dx, float* de, int32_t rows, int32_t d, int32_t vocab, void* stream) {
+  SLAM_CHECK_ARG(rows > 0 && d > 0 && vocab > 0, "embed_grad: bad shape");
+  launch_pdl(embed_grad_kernel, static_cast<unsigned>(rows), 128, 0, ST(stream), ids, mask, CBF(dx), de, d, vocab);
+  SLAM_LAUNCH_CHECK("slam_embed_grad");
   return 0;
 }
 int slam_embed_merge_bwd(const uint8_t* mask, const void* dx, void* daudio, int32_t ta, int32_t batch, int32_t s, int32_t d, void* stream) {

@@ -319,30 +319,57 @@ GROUPS = {"qkv": ("q_proj", "k_proj", "v_proj"), "o": ("o_proj",), "gu": ("gate_
 class LlamaLoRAB200:
     LORA_PREFIX = "llm.base_model.model."
 
+    BASE_PREFIX = "llm."      # reference state-dict prefix of an un-wrapped (non-peft) HF causal LM held as `slam_model.llm`
+
     def __init__(self, cfg: LlmCfg, lora: Optional[LoraCfg], arena: TrainableArena, device, weights: Optional[Dict[str, torch.Tensor]] = None,
-                 seed: int = 43, std: float = 0.02):
+                 seed: int = 43, std: float = 0.02, train_base: bool = False):
+        """train_base (train_config.freeze_llm=false, full fine-tune as in examples/s2s): every decoder parameter is an fp32 master tensor in
+        the arena under its HF name; bf16 GEMM operands (W and W^T) are re-derived from the masters at the start of every pass and the
+        backward adds a weight-gradient GEMM (dW = dY^T X on the tcgen05 kernel) per linear, bias / RMSNorm-weight / embedding gradients."""
         self.cfg, self.lora, self.arena = cfg, lora, arena
         self.device = _require_cuda(device)
+        self.train_base = bool(train_base)
+        if self.train_base and lora is not None:
+            raise NotImplementedError("full fine-tune together with LoRA adapters is not implemented (the reference recipes use one or the other)")
         dev = self.device
         L = cfg.layers
         gen = torch.Generator(device="cuda").manual_seed(seed)
+        self._init_src: Dict[str, torch.Tensor] = {}      # train_base: initial values, copied into the arena by init_base() after finalize()
 
         def base(name: str, shape) -> torch.Tensor:
             if weights is not None:
-                return weights[name].to(dev, BF16).contiguous()
-            return (torch.randn(*shape, generator=gen, device=dev, dtype=F32) * std).to(BF16)
+                t = weights[name].to(dev, F32 if self.train_base else BF16).contiguous()
+            else:
+                t = torch.randn(*shape, generator=gen, device=dev, dtype=F32) * std
+            if self.train_base:
+                self._init_src[name] = t
+            return t.to(BF16)
 
         def norm_w(name: str) -> torch.Tensor:
             if weights is not None:
-                return weights[name].to(dev, BF16).contiguous()
-            return (1.0 + torch.randn(cfg.d, generator=gen, device=dev) * std).to(BF16)
+                t = weights[name].to(dev, F32 if self.train_base else BF16).contiguous()
+            else:
+                t = 1.0 + torch.randn(cfg.d, generator=gen, device=dev) * std
+            if self.train_base:
+                self._init_src[name] = t
+            return t.to(BF16)
+
+        def bias_f32(name: str, n: int) -> torch.Tensor:
+            if weights is not None:
+                t = weights[name].to(dev, F32).contiguous()
+            else:
+                t = torch.randn(n, generator=gen, device=dev, dtype=F32) * std
+            if self.train_base:
+                self._init_src[name] = t
+            return t
 
         self.embed = base("model.embed_tokens.weight", (cfg.vocab, cfg.d))
         # Fused SwiGLU (GEMM epilogues act 3 / 4): without LoRA on gate/up the concatenated gate/up weight is stored "blocked-64"
         # (64 gate rows, then the 64 up rows of the same features, ...) so that a GEMM tile holds both halves of a feature pair.
         # With adapters on gate/up the HF [gate | up] order is kept (their gradient slices address whole projections).
         lora_targets = set(lora.targets) if lora is not None else set()
-        self.fuse_swiglu = not ({"gate_proj", "up_proj"} & lora_targets) and cfg.ffn % 64 == 0 and os.environ.get("SLAM_FUSE_SWIGLU", "1") != "0"
+        self.fuse_swiglu = (not ({"gate_proj", "up_proj"} & lora_targets) and cfg.ffn % 64 == 0 and not self.train_base
+                            and os.environ.get("SLAM_FUSE_SWIGLU", "1") != "0")      # trainable gate/up keep the HF [gate | up] order
         self.fuse_swiglu_bwd = self.fuse_swiglu and os.environ.get("SLAM_FUSE_SWIGLU_BWD", "1") != "0"
         self.layers = []
         for i in range(L):
@@ -358,12 +385,20 @@ class LlamaLoRAB200:
                 wgu = torch.cat([g_, u_], 0).contiguous()
             del g_, u_
             wd = base(p + "mlp.down_proj.weight", linear_shape(cfg, "down_proj"))
+            bqkv = None
+            if cfg.qkv_bias:                                                     # Qwen2: q/k/v biases, added in the GEMM epilogue (fp32)
+                bqkv = torch.cat([bias_f32(p + f"self_attn.{n}.bias", linear_shape(cfg, n)[0]) for n in ("q_proj", "k_proj", "v_proj")]).contiguous()
             self.layers.append(dict(wqkv=wqkv, wqkvT=ops.transpose(wqkv), wo=wo, woT=ops.transpose(wo), wgu=wgu, wguT=ops.transpose(wgu),
                                     wd=wd, wdT=ops.transpose(wd), ln1=norm_w(p + "input_layernorm.weight"),
-                                    ln2=norm_w(p + "post_attention_layernorm.weight")))
+                                    ln2=norm_w(p + "post_attention_layernorm.weight"), bqkv=bqkv))
         self.norm = norm_w("model.norm.weight")
-        self.lm_head = base("lm_head.weight", (cfg.vocab, cfg.d))
+        if cfg.tie_embeddings and (weights is None or "lm_head.weight" not in weights or self.train_base):
+            self.lm_head = self.embed                                            # tied: ONE table (and one gradient) for both uses
+        else:
+            self.lm_head = base("lm_head.weight", (cfg.vocab, cfg.d))
         self.lm_headT = ops.transpose(self.lm_head)
+        if self.train_base:
+            self._register_base(arena)
         self._rope_cache: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
 
         # ---- LoRA bookkeeping: per fused-GEMM group, rank-padded packed operands for all layers
@@ -395,6 +430,90 @@ class LlamaLoRAB200:
         self.dropout_active = False
         self.dropout_seed = seed
         self.dropout_step = 0
+
+    # ---------------------------------------------------------------------------------------- full fine-tune: fp32 masters in the arena
+    def _base_names(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """HF parameter names in ARENA ORDER: q,k,v (and their biases) and gate,up are adjacent so that the fused GEMM operands are plain
+        views of consecutive arena tensors (every size is a multiple of 8 elements, so the arena inserts no padding between them)."""
+        cfg = self.cfg
+        out = [("model.embed_tokens.weight", (cfg.vocab, cfg.d))]
+        for i in range(cfg.layers):
+            p = f"model.layers.{i}."
+            out += [(p + f"self_attn.{n}.weight", linear_shape(cfg, n)) for n in ("q_proj", "k_proj", "v_proj")]
+            if cfg.qkv_bias:
+                out += [(p + f"self_attn.{n}.bias", (linear_shape(cfg, n)[0],)) for n in ("q_proj", "k_proj", "v_proj")]
+            out += [(p + "self_attn.o_proj.weight", linear_shape(cfg, "o_proj"))]
+            out += [(p + f"mlp.{n}.weight", linear_shape(cfg, n)) for n in ("gate_proj", "up_proj")]
+            out += [(p + "mlp.down_proj.weight", linear_shape(cfg, "down_proj")), (p + "input_layernorm.weight", (cfg.d,)),
+                    (p + "post_attention_layernorm.weight", (cfg.d,))]
+        out.append(("model.norm.weight", (cfg.d,)))
+        if self.lm_head is not self.embed:
+            out.append(("lm_head.weight", (cfg.vocab, cfg.d)))
+        return out
+
+    def _register_base(self, arena: TrainableArena) -> None:
+        cfg = self.cfg
+        if cfg.d % 8 or cfg.dkv % 8 or cfg.ffn % 8:
+            raise ValueError("full fine-tune needs hidden / kv / ffn sizes that are multiples of 8 (fused arena views)")
+        for name, shape in self._base_names():
+            arena.add(self.BASE_PREFIX + name, shape)
+
+    def _fused(self, first: str, rows: int, cols: int, which: str) -> torch.Tensor:
+        """[rows, cols] (or [rows]) view over consecutive arena tensors starting at `first`."""
+        off = self.arena.offset(self.BASE_PREFIX + first)
+        buf = getattr(self.arena, which)
+        return buf[off: off + rows * max(cols, 1)].view(rows, cols) if cols else buf[off: off + rows]
+
+    def init_base(self) -> None:
+        """Copy the initial decoder weights (checkpoint or random) into the fp32 arena masters (after arena.finalize())."""
+        if not self.train_base:
+            return
+        for name, _ in self._base_names():
+            self.arena.view(self.BASE_PREFIX + name).copy_(self._init_src[name].to(F32).view(self.arena.view(self.BASE_PREFIX + name).shape))
+        self._init_src = {}
+        self.refresh_base()
+
+    def base_state(self, which: str = "param") -> Dict[str, torch.Tensor]:
+        return {self.BASE_PREFIX + n: self.arena.view(self.BASE_PREFIX + n, which) for n, _ in self._base_names()} if self.train_base else {}
+
+    def refresh_base(self) -> None:
+        """fp32 masters -> the bf16 GEMM operands W and W^T, bf16 norm weights, fp32 fused biases (once per pass: AdamW just changed them)."""
+        cfg = self.cfg
+        D, Dq, Dkv, Fd = cfg.d, cfg.dq, cfg.dkv, cfg.ffn
+
+        def both(src: torch.Tensor, w: torch.Tensor, wt: torch.Tensor) -> None:
+            r, c = src.shape
+            ops.cast_bf16(src, out=w)
+            ops.pack2d(src, wt, batch=1, rows=r, cols=c, src_bs=r * c, src_ld=c, dst_bs=r * c, dst_ld=r, transpose=True)
+
+        if self.lm_head is self.embed:
+            both(self.arena.view(self.BASE_PREFIX + "model.embed_tokens.weight"), self.embed, self.lm_headT)
+        else:
+            ops.cast_bf16(self.arena.view(self.BASE_PREFIX + "model.embed_tokens.weight"), out=self.embed)
+        for i, Lw in enumerate(self.layers):
+            p = f"model.layers.{i}."
+            both(self._fused(p + "self_attn.q_proj.weight", Dq + 2 * Dkv, D, "param"), Lw["wqkv"], Lw["wqkvT"])
+            both(self.arena.view(self.BASE_PREFIX + p + "self_attn.o_proj.weight"), Lw["wo"], Lw["woT"])
+            both(self._fused(p + "mlp.gate_proj.weight", 2 * Fd, D, "param"), Lw["wgu"], Lw["wguT"])
+            both(self.arena.view(self.BASE_PREFIX + p + "mlp.down_proj.weight"), Lw["wd"], Lw["wdT"])
+            ops.cast_bf16(self.arena.view(self.BASE_PREFIX + p + "input_layernorm.weight"), out=Lw["ln1"])
+            ops.cast_bf16(self.arena.view(self.BASE_PREFIX + p + "post_attention_layernorm.weight"), out=Lw["ln2"])
+            if cfg.qkv_bias:
+                Lw["bqkv"] = self._fused(p + "self_attn.q_proj.bias", Dq + 2 * Dkv, 0, "param")   # the fp32 master itself (epilogue reads fp32)
+        ops.cast_bf16(self.arena.view(self.BASE_PREFIX + "model.norm.weight"), out=self.norm)
+        if self.lm_head is not self.embed:
+            both(self.arena.view(self.BASE_PREFIX + "lm_head.weight"), self.lm_head, self.lm_headT)
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, first: str, rows: int, cols: int) -> None:
+        """dW [rows = out, cols = in] (fp32, into the gradient arena) = dY^T X on the tcgen05 GEMM (K = tokens, padded to a multiple of 8)."""
+        M = dy.shape[0]
+        Mp = _round_up(M, 8)
+
+        def tp(t):
+            buf = torch.zeros((t.shape[1], Mp), device=t.device, dtype=BF16) if Mp != M else torch.empty((t.shape[1], M), device=t.device, dtype=BF16)
+            ops.transpose(t, out=buf[:, :M])
+            return buf
+        ops.gemm(tp(dy), tp(x), out=self._fused(first, rows, cols, "grad"), out_f32=True)
 
     # names of the stacked arena tensors (the slam_llm mirror exposes them under the peft key names)
     @staticmethod
@@ -471,18 +590,18 @@ class LlamaLoRAB200:
         gi = list(GROUPS).index(gname)
         return (self.dropout_seed * 1000003 + self.dropout_step * 4099 + li * 8 + gi) & 0x7FFFFFFFFFFFFFFF
 
-    def _lin_fwd(self, x, w, gname: str, li: int, residual=None, out=None):
-        """y = x W^T (+ residual) + (dropout(x) A_cat^T)(s B_cat)^T  ->  (y, saved) with saved = (x_lora, T, seed) for the backward."""
+    def _lin_fwd(self, x, w, gname: str, li: int, residual=None, out=None, bias=None):
+        """y = x W^T (+ bias) (+ residual) + (dropout(x) A_cat^T)(s B_cat)^T  ->  (y, saved) with saved = (x_lora, T, seed) for the backward."""
         info = self.groups.get(gname)
         if info is None:
-            return ops.gemm(x, w, residual=residual, out=out), None
+            return ops.gemm(x, w, residual=residual, out=out, bias=bias), None
         p, seed = self.dropout_p if self.dropout_active else 0.0, 0
         x_lora = x
         if p > 0.0:
             seed = self._drop_seed(li, gname)
             x_lora = ops.dropout(x, p, seed)                                             # lora_A(dropout(x)): LoRA branch only
         t = _gemm_few_tiles(x_lora, info["a_cat"][li])                                   # T = x A_cat^T  [M, rpad]
-        y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out)       # fused base + LoRA tile
+        y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias)   # fused base + LoRA tile
         return y, (x_lora, t, p, seed)
 
     def _lin_bwd(self, dy, wT, gname: str, li: int, saved):
@@ -520,7 +639,7 @@ class LlamaLoRAB200:
         saved_layers = []
         for li, Lw in enumerate(self.layers):
             xn1, rstd1 = ops.rmsnorm_fwd(x, Lw["ln1"], cfg.eps, need_rstd=save)
-            qkv, sv_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li)
+            qkv, sv_qkv = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li, bias=Lw["bqkv"])
             ops.rope_(qkv[:, : Dq + Dkv], H + Hkv, dh, S, cos, sin)                  # q and k heads are adjacent in the fused buffer: one launch
             q = qkv[:, :Dq].view(B, S, H, dh)
             k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
@@ -539,6 +658,8 @@ class LlamaLoRAB200:
             if save:
                 saved_layers.append(dict(x=x, rstd1=rstd1, qkv=qkv, attn=attn, lse=lse, x2=x2, rstd2=rstd2, gu=gu,
                                          sv_qkv=sv_qkv, sv_o=sv_o, sv_gu=sv_gu, sv_d=sv_d))
+                if self.train_base:                                                   # inputs of the linears: the wgrad GEMMs need them
+                    saved_layers[-1].update(xn1=xn1, xn2=xn2, hmid=hmid)
             x = x3
         xf, rstd_f = ops.rmsnorm_fwd(x, self.norm, cfg.eps, need_rstd=save)
         if save:
@@ -557,18 +678,30 @@ class LlamaLoRAB200:
         scale = 1.0 / math.sqrt(dh)
         _THIN_POOL.begin(dxf.device)
         dx = ops.rmsnorm_bwd(dxf, sv["x_last"], self.norm, sv["rstd_f"])
+        tb = self.train_base
+        Fd, Dm = cfg.ffn, cfg.d
+        if tb:
+            ops.rmsnorm_wgrad(dxf, sv["x_last"], sv["rstd_f"], self.arena.view(self.BASE_PREFIX + "model.norm.weight", "grad"))
         for li in range(cfg.layers - 1, -1, -1):
             Lw, kp = self.layers[li], sv["layers"][li]
+            pn = f"model.layers.{li}."
             # ---- MLP block: x3 = x2 + down(silu(g) * u)
             if self.fuse_swiglu_bwd and "down" not in self.groups:
                 dgu = ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"])                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
             else:
                 dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
+                if tb:
+                    self._wgrad(dx, kp["hmid"], pn + "mlp.down_proj.weight", Dm, Fd)
                 dgu = ops.swiglu_bwd(kp["gu"], dhmid, block=64 if self.fuse_swiglu else 0)
             dxn2 = self._lin_bwd(dgu, Lw["wguT"], "gu", li, kp["sv_gu"])
+            if tb:
+                self._wgrad(dgu, kp["xn2"], pn + "mlp.gate_proj.weight", 2 * Fd, Dm)      # gate and up are adjacent in the arena: one GEMM
+                ops.rmsnorm_wgrad(dxn2, kp["x2"], kp["rstd2"], self.arena.view(self.BASE_PREFIX + pn + "post_attention_layernorm.weight", "grad"))
             dx2 = ops.rmsnorm_bwd(dxn2, kp["x2"], Lw["ln2"], kp["rstd2"], dres=dx)
             # ---- attention block: x2 = x + o(attn(rope(qkv(norm(x)))))
             dattn = self._lin_bwd(dx2, Lw["woT"], "o", li, kp["sv_o"])
+            if tb:
+                self._wgrad(dx2, kp["attn"].view(M, Dq), pn + "self_attn.o_proj.weight", Dm, Dq)
             qkv = kp["qkv"]
             q = qkv[:, :Dq].view(B, S, H, dh)
             k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
@@ -578,6 +711,11 @@ class LlamaLoRAB200:
                          dq=dqkv[:, :Dq].view(B, S, H, dh), dk=dqkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh), dv=dqkv[:, Dq + Dkv:].view(B, S, Hkv, dh),
                          rope=(cos, sin))                                               # inverse RoPE of dQ / dK fused into the finishing kernel
             dxn1 = self._lin_bwd(dqkv, Lw["wqkvT"], "qkv", li, kp["sv_qkv"])
+            if tb:
+                self._wgrad(dqkv, kp["xn1"], pn + "self_attn.q_proj.weight", Dq + 2 * Dkv, Dm)   # q, k, v adjacent: one GEMM
+                if cfg.qkv_bias:
+                    ops.colsum(dqkv, self._fused(pn + "self_attn.q_proj.bias", Dq + 2 * Dkv, 0, "grad"))
+                ops.rmsnorm_wgrad(dxn1, kp["x"], kp["rstd1"], self.arena.view(self.BASE_PREFIX + pn + "input_layernorm.weight", "grad"))
             dx = ops.rmsnorm_bwd(dxn1, kp["x"], Lw["ln1"], kp["rstd1"], dres=dx2)
             sv["layers"][li] = None
         return dx.view(B, S, cfg.d)
@@ -590,16 +728,18 @@ class SlamStepB200:
     """log-mel -> encoder -> projector -> merge -> decoder -> CE (+acc); backward; AdamW."""
 
     def __init__(self, enc_cfg: EncoderCfg, llm_cfg: LlmCfg, lora_cfg: Optional[LoraCfg], proj_cfg: ProjCfg, device="cuda:0",
-                 enc_weights=None, llm_weights=None, lora_weights=None, proj_weights=None, seed: int = 42, lora_b_std: float = 0.0):
+                 enc_weights=None, llm_weights=None, lora_weights=None, proj_weights=None, seed: int = 42, lora_b_std: float = 0.0,
+                 train_llm: bool = False):
         device = _require_cuda(device)
         torch.cuda.set_device(device)
         arena = TrainableArena()
         encoder = WhisperEncoderB200(enc_cfg, enc_weights, device, seed=seed)
         projector = ProjectorB200(enc_cfg, llm_cfg, proj_cfg, arena)
-        llm = LlamaLoRAB200(llm_cfg, lora_cfg, arena, device, llm_weights, seed=seed + 1)
+        llm = LlamaLoRAB200(llm_cfg, lora_cfg, arena, device, llm_weights, seed=seed + 1, train_base=train_llm)
         arena.finalize(device)
         projector.init_weights(proj_weights, seed=seed + 3)
         llm.init_lora(lora_weights, seed=seed + 2, b_std=lora_b_std)
+        llm.init_base()
         self._assemble(encoder, projector, llm, arena, device)
 
     @classmethod
@@ -631,6 +771,7 @@ class SlamStepB200:
         self.flush_update()
         out = {n: self.arena.view(n, which) for n in self.arena.names() if n.startswith(ProjectorB200.PREFIX)}
         out.update(self.llm.lora_state(which))
+        out.update(self.llm.base_state(which))
         return out
 
     def load_trainable_state(self, sd: Dict[str, torch.Tensor]) -> List[str]:
@@ -694,12 +835,14 @@ class SlamStepB200:
         x = ops.embed_merge(ids, mod_mask, aud, self.llm.embed)
         out = self.decoder_loss(x, key_mask, labels, rows=batch.get("_rows"), targets=batch.get("_targets"), train=train, full_logits=full_logits)
         if train:
-            self._ctx.update(mod_mask=mod_mask, Ta=aud.shape[1])
+            self._ctx.update(mod_mask=mod_mask, Ta=aud.shape[1], ids=ids)
         return out
 
     def begin_decoder_pass(self, train: bool) -> None:
         """Once per forward, before anything reads the trainables: land a deferred update, re-pack the adapters, arm LoRA dropout."""
         self.flush_update()
+        if self.llm.train_base:
+            self.llm.refresh_base()                                                        # full fine-tune: bf16 operands from the fp32 masters
         self.llm.pack_lora()                                                               # adapters change every optimizer step
         self.llm.dropout_active = bool(train and self.lora_dropout_enabled and self.llm.dropout_p > 0.0)
         self.llm.dropout_step += 1
@@ -727,15 +870,17 @@ class SlamStepB200:
         loss = (loss_sum / nv).squeeze(0)
         acc = (n_correct.to(F32) / nv).squeeze(0)
         if train:
-            self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, R=R)
+            self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, R=R, hsel=hsel if self.llm.train_base else None)
         return loss, acc, (logits.view(B, S, -1) if full_logits else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         """Backward of the last forward(train=True); grad_out is d(total)/d(loss) (device scalar, default 1)."""
-        mod_mask, ta = self._ctx["mod_mask"], self._ctx["Ta"]
+        mod_mask, ta, ids = self._ctx["mod_mask"], self._ctx["Ta"], self._ctx["ids"]
         self.backward_begin()
         dx = self.decoder_backward(grad_out)
+        if self.llm.train_base:                                                           # embedding rows used by the merge (slam_model.py:392)
+            ops.embed_grad(ids, mod_mask, dx.contiguous(), self.arena.view(LlamaLoRAB200.BASE_PREFIX + "model.embed_tokens.weight", "grad"))
         daud = ops.embed_merge_bwd(mod_mask, dx.contiguous(), ta)
         self.projector.backward(daud)
         self.backward_end()
@@ -764,6 +909,9 @@ class SlamStepB200:
         dlogits = torch.empty((R, V), device=dev, dtype=BF16)
         scratch = (torch.zeros(1, device=dev), torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, device=dev, dtype=torch.int32))
         ops.cross_entropy(logits, c["tgts"], scratch, dlogits, gs)
+        if self.llm.train_base:                                                            # lm_head weight gradient = dlogits^T h  (tied: lands in dE)
+            head = "model.embed_tokens.weight" if self.llm.lm_head is self.llm.embed else "lm_head.weight"
+            self.llm._wgrad(dlogits, c["hsel"], head, V, self.llm_cfg.d)
         dh = _gemm_few_tiles(dlogits, self.llm.lm_headT)                                   # [R, D], K = vocab: split-K
         M = c["B"] * c["S"]
         if c["full"]:

@@ -94,6 +94,8 @@ _SIGS = {
     "slam_scatter_rows": [_vp, _vp, _vp, _i32, _i32, _vp],
     "slam_relu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "slam_colsum": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "slam_rmsnorm_wgrad": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
+    "slam_embed_grad": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "slam_pack2d": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _vp],
     "slam_add_bf16": [_vp, _vp, _vp, _i64, _vp],
 }

@@ -464,6 +464,38 @@ def colsum(x, out):
     return out
 
 
+def colsum_add(x, out):
+    """out[c] += sum_r x[r,c] (no zeroing: accumulates into a gradient buffer that the caller cleared)."""
+    tmp = torch.empty_like(out)
+    colsum(x, tmp)
+    out.add_(tmp)
+    return out
+
+
+def rmsnorm_wgrad(dy, x, rstd, dw):
+    """dw[c] += sum_r dy[r,c] * x[r,c] * rstd[r] (f32, accumulated)."""
+    _req(dy, BF16, "rmsnorm_wgrad.dy"); _req(x, BF16, "rmsnorm_wgrad.x"); _req(rstd, F32, "rmsnorm_wgrad.rstd"); _req(dw, F32, "rmsnorm_wgrad.dw")
+    assert dy.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    assert dw.numel() == d and rstd.numel() == rows
+    _l.check(_l.load().slam_rmsnorm_wgrad(dy.data_ptr(), x.data_ptr(), rstd.data_ptr(), rows, d, dw.data_ptr(), _stream()), "slam_rmsnorm_wgrad")
+    return dw
+
+
+def embed_grad(ids, modality_mask, dx, de):
+    """dE[ids[r]] += dx[r] for rows with modality_mask == 0 (f32 atomics)."""
+    assert ids.dtype == torch.int64 and modality_mask.dtype == torch.uint8 and ids.is_contiguous() and modality_mask.is_contiguous()
+    _req(dx, BF16, "embed_grad.dx"); _req(de, F32, "embed_grad.de")
+    assert dx.is_contiguous() and de.is_contiguous()
+    d = dx.shape[-1]
+    rows = dx.numel() // d
+    assert ids.numel() == rows and de.shape[1] == d
+    _l.check(_l.load().slam_embed_grad(ids.data_ptr(), modality_mask.data_ptr(), dx.data_ptr(), de.data_ptr(), rows, d, de.shape[0], _stream()),
+             "slam_embed_grad")
+    return de
+
+
 def pack2d(src, dst, *, batch, rows, cols, src_bs, src_ld, dst_bs, dst_ld, scale=1.0, transpose=False, src_off=0, dst_off=0):
     """Batched strided f32->bf16 cast with optional transpose; offsets in elements."""
     _req(src, F32, "pack2d.src"); _req(dst, BF16, "pack2d.dst")

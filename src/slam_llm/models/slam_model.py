@@ -90,8 +90,9 @@ def random_init_allowed(model_config=None) -> bool:
 def _load_llm_cfg(llm_path: str) -> LlmCfg:
     with open(os.path.join(llm_path, "config.json")) as f:
         c = json.load(f)
-    if c.get("model_type", "llama") not in ("llama", "mistral"):
-        raise NotImplementedError(f"model_type={c.get('model_type')!r}: the B200 decoder implements the Llama architecture")
+    mt = c.get("model_type", "llama")
+    if mt not in ("llama", "mistral", "qwen2"):
+        raise NotImplementedError(f"model_type={mt!r}: the B200 decoder implements the Llama architecture (+ Qwen2's q/k/v biases and tied embeddings)")
     heads, hidden = c["num_attention_heads"], c["hidden_size"]
     # fields that change the arithmetic and are NOT implemented by the kernels: refuse instead of computing something else silently
     if c.get("rope_scaling") not in (None, {}):
@@ -100,13 +101,16 @@ def _load_llm_cfg(llm_path: str) -> LlmCfg:
         raise NotImplementedError(f"head_dim={c['head_dim']} != hidden_size/num_attention_heads={hidden // heads}")
     if c.get("attention_bias", False) or c.get("mlp_bias", False):
         raise NotImplementedError("attention_bias / mlp_bias checkpoints are not implemented by the B200 decoder (Llama linears have no bias)")
+    if mt == "qwen2" and c.get("use_sliding_window", False):
+        raise NotImplementedError("Qwen2 use_sliding_window=true: the B200 attention kernels are full causal")
     if c.get("hidden_act", "silu") != "silu":
         raise NotImplementedError(f"hidden_act={c['hidden_act']!r}: the fused MLP implements SwiGLU (silu)")
-    if c.get("sliding_window") not in (None, 0) and c.get("model_type") == "mistral":
+    if c.get("sliding_window") not in (None, 0) and mt == "mistral":
         raise NotImplementedError(f"sliding_window={c['sliding_window']}: the B200 attention kernels are full causal")
     return LlmCfg(vocab=c["vocab_size"], d=hidden, layers=c["num_hidden_layers"], heads=heads,
                   kv_heads=c.get("num_key_value_heads", heads), ffn=c["intermediate_size"],
-                  rope_theta=float(c.get("rope_theta", 10000.0)), eps=float(c.get("rms_norm_eps", 1e-5)))
+                  rope_theta=float(c.get("rope_theta", 10000.0)), eps=float(c.get("rms_norm_eps", 1e-5)),
+                  qkv_bias=(mt == "qwen2"), tie_embeddings=bool(c.get("tie_word_embeddings", False)))
 
 
 def _load_llm_weights(llm_path: str) -> Optional[Dict[str, torch.Tensor]]:
@@ -124,9 +128,7 @@ def _load_llm_weights(llm_path: str) -> Optional[Dict[str, torch.Tensor]]:
             out.update(torch.load(os.path.join(llm_path, f), map_location="cpu", weights_only=True))
     if not out:
         return None
-    if "lm_head.weight" not in out:
-        out["lm_head.weight"] = out["model.embed_tokens.weight"]                 # tie_word_embeddings
-    return out
+    return out                                                                   # (tied checkpoints carry no lm_head.weight: the engine shares the table)
 
 
 class _Embedding(nn.Module):
@@ -139,6 +141,14 @@ class _Embedding(nn.Module):
     @property
     def weight(self):
         return self._owner[0].b200.embed
+
+    def forward(self, input_ids):
+        return torch.nn.functional.embedding(input_ids.to(self.weight.device), self.weight)
+
+
+class _TrainableEmbedding(nn.Module):
+    """`llm.model.embed_tokens` of a full fine-tune: `weight` is the fp32 arena master (registered by register_views).  The fused step reads the
+    engine's bf16 copy and writes the embedding gradient itself; a recipe that calls this module directly gets an fp32, autograd-connected lookup."""
 
     def forward(self, input_ids):
         return torch.nn.functional.embedding(input_ids.to(self.weight.device), self.weight)
@@ -158,8 +168,10 @@ class LlamaB200ForCausalLM(nn.Module):
     """Frozen Llama decoder (+ optional LoRA adapters under peft-0.6 key names).  Weights are materialised when the
     module is bound to a step arena by slam_model.__init__."""
 
-    def __init__(self, cfg: LlmCfg, llm_path: str, lora_cfg, use_peft: bool, allow_random_init: bool = False, peft_ckpt: Optional[str] = None):
+    def __init__(self, cfg: LlmCfg, llm_path: str, lora_cfg, use_peft: bool, allow_random_init: bool = False, peft_ckpt: Optional[str] = None,
+                 train_base: bool = False):
         super().__init__()
+        self.train_base = train_base          # train_config.freeze_llm=false: every decoder parameter trains (fp32 masters in the arena)
         self.cfg, self.llm_path, self.lora_cfg, self.use_peft = cfg, llm_path, lora_cfg if use_peft else None, use_peft
         self.allow_random_init, self.peft_ckpt = allow_random_init, peft_ckpt
         self.b200: Optional[LlamaLoRAB200] = None
@@ -185,13 +197,15 @@ class LlamaB200ForCausalLM(nn.Module):
                 raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under llm_path={self.llm_path!r} (set model_config.b200_random_init=true "
                                         "or SLAM_B200_RANDOM_INIT=1 to benchmark with random frozen weights)")
             logger.warning(f"no weights under {self.llm_path}: RANDOM-INIT {self.cfg} (b200_random_init)")
-        self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights, seed=seed + 1)
+        if weights is not None and "lm_head.weight" not in weights and not self.cfg.tie_embeddings:
+            weights["lm_head.weight"] = weights["model.embed_tokens.weight"]      # checkpoint saved with tied weights but an untied config
+        self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights, seed=seed + 1, train_base=self.train_base)
 
     def register_views(self, arena: TrainableArena) -> None:
         """Expose the embedding module and the LoRA adapters under the reference / peft key names."""
         causal = nn.Module()          # LlamaForCausalLM
         inner = nn.Module()           # LlamaModel
-        inner.add_module("embed_tokens", _Embedding(self))
+        inner.add_module("embed_tokens", _TrainableEmbedding() if self.train_base else _Embedding(self))
         causal.add_module("model", inner)
         if self.use_peft:
             lora_model = nn.Module()  # peft LoraModel
@@ -201,6 +215,9 @@ class LlamaB200ForCausalLM(nn.Module):
                 _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
         else:
             self.add_module("model", causal)
+        if self.train_base:           # full fine-tune: HF parameter names over the fp32 arena masters (`llm.model.layers.N...`, `llm.lm_head.weight`)
+            for key, view in self.b200.base_state().items():
+                _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
 
     def print_trainable_parameters(self):
         trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -220,8 +237,9 @@ def setup_llm(train_config, model_config, **kwargs):
     """slam_model.py:118-221: frozen base LLM + LoRA adapters from train_config.peft_config."""
     if train_config.quantization:
         raise NotImplementedError("8-bit quantised loading is out of scope of the B200 path")
-    if not train_config.freeze_llm:
-        raise NotImplementedError("freeze_llm=false (full fine-tune) needs wgrad for every linear: SURVEY.md §8f rank 3, not built yet")
+    train_base = not train_config.freeze_llm                        # full fine-tune (examples/s2s): slam_model.py:205-208 not taken
+    if train_base and (train_config.use_peft or kwargs.get("peft_ckpt", None)):
+        raise NotImplementedError("freeze_llm=false together with peft adapters is not implemented (the reference recipes use one or the other)")
     cfg = _load_llm_cfg(model_config.llm_path)
     peft_ckpt = kwargs.get("peft_ckpt", None)
     if peft_ckpt:                                                    # slam_model.py:210-213: PeftModel.from_pretrained(model, peft_ckpt, is_trainable=True)
@@ -231,7 +249,7 @@ def setup_llm(train_config, model_config, **kwargs):
         lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
     use_peft = bool(peft_ckpt) or bool(train_config.use_peft)
     model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, use_peft, allow_random_init=random_init_allowed(model_config),
-                                 peft_ckpt=peft_ckpt or None)
+                                 peft_ckpt=peft_ckpt or None, train_base=train_base)
     print_module_size(model, model_config.llm_name, _rank(train_config))
     model.eval()
     if train_config.use_peft and not peft_ckpt:
@@ -353,6 +371,7 @@ class slam_model(nn.Module):
         arena.finalize(device)
         encoder_projector.bind(eng_proj, arena)
         llm.b200.init_lora(None, seed=seed + 2)                     # peft init: A kaiming-uniform, B zeros
+        llm.b200.init_base()                                        # full fine-tune: checkpoint weights -> fp32 arena masters
         llm.register_views(arena)
         if llm.peft_ckpt:
             sd = _peft_dir_state(llm.peft_ckpt)

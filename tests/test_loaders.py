@@ -23,10 +23,13 @@ def test_llm_config_reader_rejects_what_the_kernels_do_not_implement(tmp_path):
     cfg = _load_llm_cfg(_cfg_dir(tmp_path))
     assert (cfg.vocab, cfg.d, cfg.layers, cfg.heads, cfg.kv_heads, cfg.ffn) == (512, 256, 2, 4, 2, 512)
     for bad in (dict(rope_scaling={"rope_type": "llama3", "factor": 8.0}), dict(head_dim=32), dict(attention_bias=True), dict(mlp_bias=True),
-                dict(hidden_act="gelu"), dict(model_type="mistral", sliding_window=4096), dict(model_type="qwen2")):
+                dict(hidden_act="gelu"), dict(model_type="mistral", sliding_window=4096), dict(model_type="gemma"),
+                dict(model_type="qwen2", use_sliding_window=True)):
         with pytest.raises(NotImplementedError):
             _load_llm_cfg(_cfg_dir(tmp_path, **bad))
     assert _load_llm_cfg(_cfg_dir(tmp_path, head_dim=64, rope_scaling=None)).d == 256
+    q = _load_llm_cfg(_cfg_dir(tmp_path, model_type="qwen2", tie_word_embeddings=True, rms_norm_eps=1e-6, rope_theta=1e6))
+    assert q.qkv_bias and q.tie_embeddings and q.eps == 1e-6 and not cfg.qkv_bias and not cfg.tie_embeddings
 
 
 def test_llm_weight_reader_safetensors_bin_and_tied_head(tmp_path):
@@ -46,7 +49,7 @@ def test_llm_weight_reader_safetensors_bin_and_tied_head(tmp_path):
     tied = {k: v for k, v in w.items() if k != "lm_head.weight"}
     torch.save(tied, str(b / "pytorch_model.bin"))
     got = _load_llm_weights(str(b))
-    assert torch.equal(got["lm_head.weight"], w["model.embed_tokens.weight"])
+    assert "lm_head.weight" not in got and torch.equal(got["model.embed_tokens.weight"], w["model.embed_tokens.weight"])   # tied: the engine shares the table
     e = tmp_path / "empty"
     e.mkdir()
     assert _load_llm_weights(str(e)) is None

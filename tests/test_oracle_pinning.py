@@ -161,3 +161,28 @@ def test_lora_branch_matches_peft_formula_and_grads():
     assert torch.allclose(y.detach(), x @ W.t() + s * (x @ A.t()) @ Bm.t(), atol=1e-5)
     assert torch.allclose(Bm.grad, s * dy.t() @ (x @ A.t()).detach(), atol=1e-5)
     assert torch.allclose(A.grad, s * (dy @ Bm.detach()).t() @ x, atol=1e-5)
+
+
+def test_qwen2_style_decoder_matches_hf_qwen2():
+    """q/k/v biases + tied embeddings (the s2s recipes' Qwen2-0.5B): the oracle's decoder vs HF Qwen2ForCausalLM (eager)."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    cfg = so.LlmCfg(300, 128, 2, 4, 2, 256, 1e6, 1e-6, True, True)
+    w = so.init_llm(cfg, seed=3)
+    assert "lm_head.weight" not in w and "model.layers.0.self_attn.q_proj.bias" in w and "model.layers.0.self_attn.o_proj.bias" not in w
+    hc = Qwen2Config(vocab_size=cfg.vocab, hidden_size=cfg.d, intermediate_size=cfg.ffn, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+                     num_key_value_heads=cfg.kv_heads, rms_norm_eps=cfg.eps, rope_theta=cfg.rope_theta, tie_word_embeddings=True,
+                     max_position_embeddings=512, use_sliding_window=False, attn_implementation="eager")
+    m = Qwen2ForCausalLM(hc).eval()
+    missing, unexpected = m.load_state_dict(w, strict=False)
+    assert not unexpected and set(missing) <= {"lm_head.weight"}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 17, cfg.d, generator=g)
+    att = torch.ones(2, 17, dtype=torch.bool)
+    att[0, :3] = False
+    labels = torch.randint(0, cfg.vocab, (2, 17), generator=g)
+    labels[:, :5] = -100
+    out = m(inputs_embeds=x, attention_mask=att, labels=labels)
+    lg = so.llama_forward(w, {}, cfg, None, x, att)
+    sel = att[:, :, None].expand_as(lg)
+    assert (lg[sel] - out.logits[sel]).abs().max().item() < 2e-4
+    assert abs(so.causal_lm_loss(lg, labels).item() - out.loss.item()) < 1e-5
