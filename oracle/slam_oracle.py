@@ -525,6 +525,87 @@ class OracleModel:
                 "encoder_out": out["encoder_out"], "audio_tokens": out["audio_tokens"].detach(), "inputs_embeds": out["inputs_embeds"].detach()}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# f3  SLAM-Omni (s2s) head: multi-layer token input, group CE  (examples/s2s/model/slam_model_s2s.py:160-306)
+# ------------------------------------------------------------------------------------------------------------------
+
+
+def s2s_forward(om: "OracleModel", batch: Dict[str, torch.Tensor], code_layer: int, text_vocab: int, audio_vocab: int):
+    """input_ids / labels are [B, code_layer + 1, S]: `code_layer` audio-codebook layers + one text layer (slam_model_s2s.py:220-268).
+    Embeddings of all layers are averaged (the audio features replace the masked span in the audio layers only), the decoder's logits over the
+    expanded vocabulary are split into a text slice and code_layer audio slices, and the loss is the mean of the code_layer + 1 shifted CEs
+    (compute_parallel_loss, :285-306).  Returns (loss, text_acc, layer_losses, logits)."""
+    mel = batch.get("audio_mel")
+    if mel is None:
+        mel = batch_log_mel(batch["audio_pcm"], om.enc_cfg.n_mels, batch.get("audio_pcm_lengths"))
+    with torch.no_grad():
+        enc = whisper_encoder(om.enc_w, om.enc_cfg, mel)
+    aud = projector(om.proj_w, om.proj_cfg, enc)
+    ids = batch["input_ids"].clone()
+    ids[ids == -1] = 0
+    emb = F.embedding(ids, om.llm_w["model.embed_tokens.weight"])                       # [B, L+1, S, D]
+    mm = batch["modality_mask"].bool().unsqueeze(1).repeat(1, code_layer, 1)             # [B, L, S]
+    start = (mm == True).float().argmax(dim=2)                                          # noqa: E712
+    lengths = torch.clamp(mm.sum(dim=2), max=aud.shape[1]).tolist()
+    pad = torch.zeros_like(emb)
+    for i in range(aud.shape[0]):
+        for j in range(code_layer):
+            s0, n = start[i, j].item(), lengths[i][j]
+            pad[i, j, s0:s0 + n] = aud[i, :n]
+    emb = torch.cat([pad[:, :code_layer] + emb[:, :code_layer] * (~mm[:, :, :, None]), emb[:, code_layer:]], dim=1)
+    x = emb.mean(dim=1)
+    logits = llama_forward(om.llm_w, om.lora_w, om.llm_cfg, om.lora_cfg, x, batch["attention_mask"])
+    labels = batch["labels"]
+    text_labels, audio_labels = labels[:, code_layer], labels[:, :code_layer]
+    xt = logits[..., :text_vocab]
+    layer_loss = [None] * (code_layer + 1)
+    layer_loss[code_layer] = F.cross_entropy(xt[:, :-1].reshape(-1, text_vocab), text_labels[:, 1:].reshape(-1), ignore_index=-100)
+    total = layer_loss[code_layer]
+    for i in range(code_layer):
+        xa = logits[..., text_vocab + audio_vocab * i: text_vocab + audio_vocab * (i + 1)]
+        layer_loss[i] = F.cross_entropy(xa[:, :-1].reshape(-1, audio_vocab), audio_labels[:, i, 1:].reshape(-1), ignore_index=-100)
+        total = total + layer_loss[i]
+    loss = total / (code_layer + 1)
+    text_acc = compute_accuracy(torch.argmax(xt, -1)[:, :-1], text_labels[:, 1:], ignore_label=-100)
+    return loss, text_acc, layer_loss, logits
+
+
+def s2s_step(om: "OracleModel", batch, code_layer: int, text_vocab: int, audio_vocab: int):
+    params = om.trainable()
+    for p in params.values():
+        p.requires_grad_(True)
+        p.grad = None
+    loss, acc, layer_loss, logits = s2s_forward(om, batch, code_layer, text_vocab, audio_vocab)
+    loss.backward()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    for p in params.values():
+        p.requires_grad_(False)
+    return {"loss": loss.detach(), "acc": acc, "layer_loss": [l.detach() for l in layer_loss], "grads": grads, "logits": logits.detach()}
+
+
+def s2s_synthetic_batch(B: int, n_samples: int, code_layer: int, text_vocab: int, audio_vocab: int, k: int = 5, prompt_len: int = 5, answer_len: int = 8,
+                        seed: int = 42) -> Dict[str, torch.Tensor]:
+    """[audio(-1)*Ta, prompt, answer] in code_layer + 1 parallel token layers: layer i < code_layer draws from its own audio-code slice of the
+    expanded vocabulary, the last layer from the text vocabulary; labels -100 outside the answer span (all layers)."""
+    g = torch.Generator().manual_seed(seed)
+    wav = torch.randn(B, n_samples, generator=g) * 0.1
+    ta = ((n_samples // 160 + 1) // 2) // k
+    S = ta + prompt_len + answer_len
+    ids = torch.zeros(B, code_layer + 1, S, dtype=torch.int64)
+    labels = torch.zeros(B, code_layer + 1, S, dtype=torch.int64)
+    for i in range(code_layer):
+        codes = torch.randint(0, audio_vocab, (B, S), generator=g)
+        ids[:, i] = text_vocab + audio_vocab * i + codes              # inputs index the expanded table (layer shift) ...
+        labels[:, i] = codes                                          # ... targets index the layer's own slice of the logits
+    ids[:, code_layer] = labels[:, code_layer] = torch.randint(0, text_vocab, (B, S), generator=g)
+    labels[:, :, : ta + prompt_len] = -100
+    ids[:, :, :ta] = -1
+    att = torch.ones(B, S, dtype=torch.bool)
+    mod = torch.zeros(B, S, dtype=torch.bool)
+    mod[:, :ta] = True
+    return {"input_ids": ids, "labels": labels, "attention_mask": att, "modality_mask": mod, "audio_pcm": wav}
+
+
 def lr_lambda(step: int, warmup: int, total: int) -> float:
     """src/slam_llm/pipeline/finetune.py:253-260."""
     if step < warmup:

@@ -896,9 +896,11 @@ class SlamStepB200:
             self._carry = None
         self.micro_steps += 1
 
-    def decoder_backward(self, grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def decoder_backward(self, grad_out: Optional[torch.Tensor] = None, grad_logits: Optional[torch.Tensor] = None) -> torch.Tensor:
         """CE + lm_head + decoder backward of the last decoder_loss(train=True): LoRA gradients into the arena, returns d loss / d inputs_embeds
-        bf16 [B,S,D] (call between backward_begin() and backward_end())."""
+        bf16 [B,S,D] (call between backward_begin() and backward_end()).  grad_logits (f32 [B,S,V] or [B*S,V], full-logits mode only): an
+        upstream gradient w.r.t. the returned logits (recipes that compute their own loss from `outputs.logits`, e.g. the s2s group CE);
+        it is added to the CE term (grad_out = 0 drops the CE term)."""
         c = self._ctx
         self._ctx = None
         dev = self.device
@@ -909,6 +911,10 @@ class SlamStepB200:
         dlogits = torch.empty((R, V), device=dev, dtype=BF16)
         scratch = (torch.zeros(1, device=dev), torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, device=dev, dtype=torch.int32))
         ops.cross_entropy(logits, c["tgts"], scratch, dlogits, gs)
+        if grad_logits is not None:
+            if not c["full"]:
+                raise RuntimeError("a gradient w.r.t. logits needs the full-logits mode (train_config.b200_full_logits=true)")
+            dlogits = ops.add(dlogits, ops.cast_bf16(grad_logits.to(dev, F32).reshape(R, V).contiguous()))
         if self.llm.train_base:                                                            # lm_head weight gradient = dlogits^T h  (tied: lands in dE)
             head = "model.embed_tokens.weight" if self.llm.lm_head is self.llm.embed else "lm_head.weight"
             self.llm._wgrad(dlogits, c["hsel"], head, V, self.llm_cfg.d)

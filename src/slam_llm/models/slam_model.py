@@ -188,6 +188,10 @@ class LlamaB200ForCausalLM(nn.Module):
                 mods = self.__dict__.get("_modules", {})
                 if "base_model" in mods:
                     return mods["base_model"]._modules["model"]
+            if name == "lm_head":                     # frozen / tied head: an object with `.weight` [vocab, hidden] (the engine's bf16 table)
+                b200 = self.__dict__.get("b200")
+                w = b200.lm_head if b200 is not None else torch.empty(self.cfg.vocab, self.cfg.d, device="meta")
+                return types.SimpleNamespace(weight=w)
             raise
 
     def bind(self, arena: TrainableArena, device, seed: int = 42) -> None:
@@ -199,6 +203,12 @@ class LlamaB200ForCausalLM(nn.Module):
             logger.warning(f"no weights under {self.llm_path}: RANDOM-INIT {self.cfg} (b200_random_init)")
         if weights is not None and "lm_head.weight" not in weights and not self.cfg.tie_embeddings:
             weights["lm_head.weight"] = weights["model.embed_tokens.weight"]      # checkpoint saved with tied weights but an untied config
+        if weights is not None:
+            g = torch.Generator().manual_seed(seed + 7)
+            for k in ("model.embed_tokens.weight", "lm_head.weight"):             # grown vocabulary: new rows ~ N(0, 0.02) (HF _init_weights)
+                if k in weights and weights[k].shape[0] < self.cfg.vocab:
+                    extra = torch.randn(self.cfg.vocab - weights[k].shape[0], weights[k].shape[1], generator=g) * 0.02
+                    weights[k] = torch.cat([weights[k].float(), extra], 0)
         self.b200 = LlamaLoRAB200(self.cfg, self.lora_cfg, arena, device, weights, seed=seed + 1, train_base=self.train_base)
 
     def register_views(self, arena: TrainableArena) -> None:
@@ -218,6 +228,17 @@ class LlamaB200ForCausalLM(nn.Module):
         if self.train_base:           # full fine-tune: HF parameter names over the fp32 arena masters (`llm.model.layers.N...`, `llm.lm_head.weight`)
             for key, view in self.b200.base_state().items():
                 _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
+
+    # ---- HF surface the s2s recipe touches (examples/s2s/model/slam_model_s2s.py:146-151)
+    # (`self.llm.lm_head.weight.size(0)` resolves through __getattr__ below when no trainable lm_head parameter is registered)
+    def resize_token_embeddings(self, new_num_tokens: int):
+        """The B200 decoder sizes its tables at construction: setup_llm reads `model_config.vocab_config.total_vocabsize` (the value the s2s recipe
+        passes here) and grows the vocabulary up front, new rows ~ N(0, 0.02) like HF's _init_weights.  A later resize is therefore a no-op
+        check."""
+        if int(new_num_tokens) != self.cfg.vocab:
+            raise NotImplementedError(f"resize_token_embeddings({new_num_tokens}) after construction (vocab {self.cfg.vocab}): set "
+                                      "model_config.vocab_config.total_vocabsize so that the decoder is built at the final size")
+        return self
 
     def print_trainable_parameters(self):
         trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -248,6 +269,13 @@ def setup_llm(train_config, model_config, **kwargs):
     else:
         lora_cfg = generate_peft_config(train_config) if train_config.use_peft else None
     use_peft = bool(peft_ckpt) or bool(train_config.use_peft)
+    vc = model_config.get("vocab_config", None)
+    total_vocab = int(vc.get("total_vocabsize", 0)) if vc is not None else 0
+    if total_vocab and total_vocab != cfg.vocab:                    # s2s: text vocab + code_layer audio vocabularies (slam_model_s2s.py:146-151)
+        if total_vocab < cfg.vocab:
+            raise ValueError(f"vocab_config.total_vocabsize={total_vocab} is smaller than the checkpoint vocabulary {cfg.vocab}")
+        logger.info(f"growing the LLM vocabulary {cfg.vocab} -> {total_vocab} (model_config.vocab_config.total_vocabsize)")
+        cfg.vocab_ckpt, cfg.vocab = cfg.vocab, total_vocab
     model = LlamaB200ForCausalLM(cfg, model_config.llm_path, lora_cfg, use_peft, allow_random_init=random_init_allowed(model_config),
                                  peft_ckpt=peft_ckpt or None, train_base=train_base)
     print_module_size(model, model_config.llm_name, _rank(train_config))
@@ -328,17 +356,20 @@ class _LlmLoss(torch.autograd.Function):
         x = inputs_embeds.detach().to(eng.device, torch.bfloat16).contiguous()
         loss, acc, logits = eng.decoder_loss(x, key_mask, labels, train=True, full_logits=full)
         ctx.owner, ctx.in_dtype = owner, inputs_embeds.dtype
+        ctx.set_materialize_grads(False)
         if logits is None:
             logits = torch.empty(0, device=eng.device)
-        ctx.mark_non_differentiable(logits)
-        return loss.clone(), logits
+            ctx.mark_non_differentiable(logits)                    # labelled-rows mode: only the loss is differentiable
+        return loss.clone(), logits                                # full-logits mode: BOTH outputs are differentiable (s2s builds its own loss)
 
     @staticmethod
-    def backward(ctx, grad_loss, _grad_logits):
+    def backward(ctx, grad_loss, grad_logits):
         owner = ctx.owner
         eng = owner.b200
         eng.backward_begin()
-        dx = eng.decoder_backward(grad_loss)
+        if grad_loss is None:                                      # the recipe ignored outputs.loss: no CE term
+            grad_loss = torch.zeros((), device=eng.device)
+        dx = eng.decoder_backward(grad_loss, grad_logits=grad_logits)
         torch.autograd.Variable._execution_engine.queue_callback(owner._finish_split_backward)
         return dx.to(ctx.in_dtype), None, None, None, None
 
@@ -448,11 +479,18 @@ class slam_model(nn.Module):
             eng.begin_decoder_pass(False)
             loss, acc, logits = eng.decoder_loss(inputs_embeds.detach().to(dev, torch.bfloat16).contiguous(), key_mask, labels, train=False, full_logits=full)
             return _Outputs(loss=loss, logits=logits)
+        for p in self.parameters():                                # arena views are re-bound after the backward (_finish_split_backward)
+            p.grad = None
         loss, logits = _LlmLoss.apply(inputs_embeds, self, key_mask, labels, full)
-        return _Outputs(loss=loss, logits=logits)
+        return _Outputs(loss=loss, logits=logits if logits.numel() else None)
 
     def _finish_split_backward(self):
-        """Runs once the autograd pass that contained _LlmLoss.backward has finished (projector node included)."""
+        """Runs once the autograd pass that contained _LlmLoss.backward has finished (projector / embedding nodes included)."""
+        grads = self.b200.trainable_state("grad")
+        for name, p in self.named_parameters():                    # a torch node (e.g. the trainable embedding lookup) left a gradient tensor of
+            g = p.grad                                             # its own: fold it into the arena, which is what the optimizer reads
+            if g is not None and name in grads and g.data_ptr() != grads[name].data_ptr():
+                grads[name].add_(g.to(grads[name].dtype).view_as(grads[name]))
         self.b200.backward_end()
         if self.ddp_world_size > 1 and self.ddp_sync:
             self.b200.allreduce_grads(async_op=self.b200.defer_update)
