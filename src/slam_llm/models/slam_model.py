@@ -224,7 +224,7 @@ class LlamaB200ForCausalLM(nn.Module):
             for key, view in self.b200.lora_state().items():
                 _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
         else:
-            self.add_module("model", causal)
+            self.add_module("model", inner)       # un-wrapped: this module IS the HF causal LM (`llm.model` = LlamaModel, `llm.lm_head`)
         if self.train_base:           # full fine-tune: HF parameter names over the fp32 arena masters (`llm.model.layers.N...`, `llm.lm_head.weight`)
             for key, view in self.b200.base_state().items():
                 _set_param(self, key[len("llm."):], nn.Parameter(view, requires_grad=True))
