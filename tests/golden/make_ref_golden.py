@@ -187,6 +187,78 @@ def build_reference_model(case, om, tmp, mods, tokenizer):
     return model
 
 
+S2S = dict(code_layer=3, text_vocab=400, audio_vocab=80, enc=(80, 1500, 128, 2, 1), llm=(640, 256, 2, 4, 1, 384, 1000000.0, 1e-6, True, True),
+           proj=("linear", 5, 2048), seed=21, batch_seed=5)
+
+
+def reference_s2s_step() -> dict:
+    """The reference's OWN SLAM-Omni model class (examples/s2s/model/slam_model_s2s.py: forward :160-283 + compute_parallel_loss :285-306) over
+    an HF Qwen2ForCausalLM built by the reference's setup_llm with freeze_llm=false (full fine-tune), the reference encoder / projector
+    factories, on the oracle's synthetic s2s batch (CPU mel from the whisper stand-in)."""
+    import importlib
+    import whisper
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    mods = ref_glue.reference_modules()
+    sys.path.insert(0, "/root/reference/examples/s2s")
+    s2s_mod = importlib.import_module("model.slam_model_s2s")
+    assert s2s_mod.__file__.startswith("/root/reference/")
+    L, TV, AV = S2S["code_layer"], S2S["text_vocab"], S2S["audio_vocab"]
+    enc, llm, proj = so.EncoderCfg(*S2S["enc"]), so.LlmCfg(*S2S["llm"]), so.ProjCfg(*S2S["proj"])
+    assert llm.vocab == TV + L * AV
+    om = round_frozen(so.OracleModel.build(enc, llm, None, proj, seed=S2S["seed"]))
+    torch.manual_seed(0)
+    with tempfile.TemporaryDirectory() as tmp:
+        wpt = os.path.join(tmp, "whisper_enc.pt")
+        torch.save(ref_glue.whisper_checkpoint(om.enc_w, enc.n_mels, enc.n_ctx, enc.d, enc.heads, enc.layers), wpt)
+        hf_dir = os.path.join(tmp, "llm")
+        hc = Qwen2Config(vocab_size=llm.vocab, hidden_size=llm.d, intermediate_size=llm.ffn, num_hidden_layers=llm.layers, num_attention_heads=llm.heads,
+                         num_key_value_heads=llm.kv_heads, rms_norm_eps=llm.eps, rope_theta=llm.rope_theta, tie_word_embeddings=True,
+                         max_position_embeddings=4096, use_sliding_window=False, attn_implementation="eager")
+        hf = Qwen2ForCausalLM(hc)
+        missing, unexpected = hf.load_state_dict(om.llm_w, strict=False)
+        assert not unexpected and set(missing) <= {"lm_head.weight"}, (missing, unexpected)
+        hf.save_pretrained(hf_dir, safe_serialization=True)
+        del hf
+        train_config = OmegaConf.create(dict(enable_fsdp=False, enable_ddp=False, low_cpu_fsdp=False, quantization=False, use_fast_kernels=False,
+                                             freeze_llm=False, freeze_encoder=True, use_peft=False, task_type="s2s"))
+        model_config = OmegaConf.create(dict(llm_name="qwen2", llm_path=hf_dir, llm_dim=llm.d, encoder_name="whisper", encoder_path=wpt,
+                                             encoder_path_hf=None, whisper_decode=False, encoder_dim=enc.d, encoder_projector=proj.kind,
+                                             encoder_projector_ds_rate=proj.k,
+                                             vocab_config=dict(code_layer=L, padded_text_vocabsize=TV, padded_audio_vocabsize=AV, total_vocabsize=llm.vocab)))
+        sm = mods["slam_model"]
+
+        class _AutoCausalLM435:
+            @staticmethod
+            def from_pretrained(path, **kw):
+                from transformers import AutoModelForCausalLM
+                return AutoModelForCausalLM.from_pretrained(path, attn_implementation="eager", torch_dtype=torch.float32,
+                                                            **{k: v for k, v in kw.items() if v is not None})
+        sm.AutoModelForCausalLM = _AutoCausalLM435
+        encoder = sm.setup_encoder(train_config, model_config)
+        llm_mod = sm.setup_llm(train_config, model_config)
+        projector = sm.setup_encoder_projector(train_config, model_config)
+        model = s2s_mod.slam_model_s2s(encoder, llm_mod, projector, None, None, None, None, None, train_config, model_config)
+    sd = {f"encoder_projector.{k}": v for k, v in om.proj_w.items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected
+    model.train()
+    batch = so.s2s_synthetic_batch(2, 32000, L, TV, AV, seed=S2S["batch_seed"])
+    mel = torch.stack([whisper.log_mel_spectrogram(w, n_mels=enc.n_mels).permute(1, 0) for w in batch["audio_pcm"]])
+    feed = dict(input_ids=batch["input_ids"].clone(), attention_mask=batch["attention_mask"], labels=batch["labels"], modality_mask=batch["modality_mask"],
+                audio_mel=mel)
+    outputs, text_acc, audio_acc, layer_loss = model(**feed)
+    outputs.loss.backward()
+    trainable = {n: p for n, p in model.named_parameters() if p.requires_grad}
+    grads = {}
+    for n, p in trainable.items():
+        if n == "llm.lm_head.weight":                                   # tied: the same tensor as the embedding (HF lists it once)
+            continue
+        g = p.grad.detach() if p.grad is not None else torch.zeros_like(p)
+        grads[n] = g.clone() if g.numel() <= 70000 else probe(g, 4096)
+    return dict(case="s2s", cfg=S2S, loss=outputs.loss.item(), text_acc=float(text_acc), layer_loss=[float(l) for l in layer_loss], grads=grads,
+                mel=probe(mel, 512), logits=probe(outputs.logits.detach(), 2048), trainable=sorted(grads))
+
+
 def probe(t: torch.Tensor, n: int = 256):
     t = t.detach().float()
     return dict(norm=t.norm().item(), head=t.flatten()[:n].clone(), shape=tuple(t.shape))
@@ -316,6 +388,7 @@ def main():
     args = ap.parse_args()
     todo = {f"ref_{c}.pt": (lambda c=c: reference_step(c)) for c in CASES}
     todo["ref_collator.pt"] = collator_cases
+    todo["ref_s2s.pt"] = reference_s2s_step
     for name, fn in todo.items():
         if args.only and args.only not in name:
             continue

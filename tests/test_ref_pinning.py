@@ -78,6 +78,34 @@ def test_oracle_matches_reference_run_at_real_widths():
     _oracle_vs_fixture(rf.load("ref_realwidth.pt"), small=False)
 
 
+def test_oracle_s2s_matches_the_reference_s2s_model():
+    """tests/golden/ref_s2s.pt = the reference's OWN examples/s2s/model/slam_model_s2s.py (forward + compute_parallel_loss) over HF Qwen2ForCausalLM,
+    full fine-tune; the oracle's s2s_forward / s2s_step must reproduce loss, per-layer losses, accuracy and the gradient of every parameter."""
+    fix = rf.load("ref_s2s.pt")
+    c = fix["cfg"]
+    L, TV, AV = c["code_layer"], c["text_vocab"], c["audio_vocab"]
+    enc, llm, proj = so.EncoderCfg(*c["enc"]), so.LlmCfg(*c["llm"]), so.ProjCfg(*c["proj"])
+    from parity_util import round_frozen
+    om = round_frozen(so.OracleModel.build(enc, llm, None, proj, seed=c["seed"]))
+    om.train_llm = True
+    batch = so.s2s_synthetic_batch(2, 32000, L, TV, AV, seed=c["batch_seed"])
+    ref = so.s2s_step(om, batch, L, TV, AV)
+    assert abs(ref["loss"].item() - fix["loss"]) <= 1e-5 * abs(fix["loss"]), (ref["loss"].item(), fix["loss"])
+    for got, want in zip(ref["layer_loss"], fix["layer_loss"]):
+        assert abs(got.item() - want) <= 1e-5 * abs(want)
+    assert abs(float(ref["acc"]) - fix["text_acc"]) < 1e-7
+    rf.check_probe(ref["logits"], fix["logits"], norm_rel=1e-5, head_rel=1e-4, what="logits")
+    assert set(ref["grads"]) == set(fix["grads"]), sorted(set(ref["grads"]) ^ set(fix["grads"]))
+    gmax = max((g["norm"] if rf.is_probe(g) else g.norm().item()) for g in fix["grads"].values())
+    for k, g_ref in fix["grads"].items():
+        g = ref["grads"][k]
+        if rf.is_probe(g_ref):
+            if g_ref["norm"] >= 1e-6 * gmax:
+                rf.check_probe(g, g_ref, norm_rel=1e-4, head_rel=5e-4, what=k)
+        elif g_ref.norm().item() >= 1e-6 * gmax:
+            assert rf.rel_l2(g, g_ref) < 1e-4, (k, rf.rel_l2(g, g_ref))
+
+
 def test_realwidth_fixture_is_the_baseline_shape():
     fix = rf.load("ref_realwidth.pt")
     enc, llm, lora, proj = rf.cfgs(fix)
@@ -181,7 +209,7 @@ def test_dynamic_dataset_mirror_reproduces_the_reference_batches(tmp_path):
 def test_fixtures_regenerate_from_the_reference_code():
     """Re-run the reference's own code (dedicated process: its `slam_llm` package shadows this repo's mirror) and compare with the
     committed fixtures.  The real-width case is left to `make_ref_golden.py --check --only realwidth` (3 min)."""
-    for only in ("tiny", "collator"):          # "tiny" matches ref_tiny, ref_tiny_cov1d_all and ref_tiny_dynamic
+    for only in ("tiny", "collator", "s2s"):   # "tiny" matches ref_tiny, ref_tiny_cov1d_all and ref_tiny_dynamic
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_ref_golden.py"), "--check", "--only", only],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -84,6 +84,19 @@ def test_s2s_style_recipe_full_finetune_matches_oracle(tmp_path):
         assert cosine(g, g_ref) > 0.99 and rel_l2(g, g_ref) < 3e-2, (k, cosine(g, g_ref), rel_l2(g, g_ref))
         checked += 1
     assert checked >= 15, checked
+    # ... and with what the REFERENCE'S OWN slam_model_s2s produced on the CPU for this configuration (tests/golden/ref_s2s.pt)
+    import ref_fixture as rf
+    fix = rf.load("ref_s2s.pt")
+    assert fix["cfg"]["seed"] == 21 and fix["cfg"]["batch_seed"] == 5 and tuple(fix["cfg"]["llm"]) == tuple(vars(cfg).values())
+    assert abs(outputs.loss.item() - fix["loss"]) <= 5e-3 * abs(fix["loss"]), (outputs.loss.item(), fix["loss"])
+    fmax = max((g["norm"] if rf.is_probe(g) else g.norm().item()) for g in fix["grads"].values())
+    for k, g_ref in fix["grads"].items():
+        g = named[k].grad
+        if rf.is_probe(g_ref):
+            if g_ref["norm"] >= 1e-3 * fmax:
+                rf.check_probe(g, g_ref, norm_rel=3e-2, head_cos=0.99, what=k)
+        elif g_ref.norm().item() >= 1e-3 * fmax:
+            assert cosine(g, g_ref) > 0.99 and rel_l2(g, g_ref) < 3e-2, (k, cosine(g, g_ref), rel_l2(g, g_ref))
     # p.grad are arena views again; one optimizer step lowers the recipe's loss
     assert named["llm.model.embed_tokens.weight"].grad.data_ptr() == model.b200.trainable_state("grad")["llm.model.embed_tokens.weight"].data_ptr()
     opt = FlatAdamW(model, lr=1e-3)
