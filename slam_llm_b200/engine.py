@@ -873,6 +873,15 @@ class SlamStepB200:
             self._ctx = dict(logits=logits, tgts=tgts, rows=rows, full=full_logits, nv=nv, B=B, S=S, R=R, hsel=hsel if self.llm.train_base else None)
         return loss, acc, (logits.view(B, S, -1) if full_logits else None)
 
+    def decoder_last_logits(self, x: torch.Tensor, key_mask: torch.Tensor) -> torch.Tensor:
+        """Next-token logits of a batch of sequences (decode path, slam_model.generate): decoder forward on bf16 [n,S,D] with the key mask,
+        lm_head on the LAST position of every sequence only -> f32 [n, V].  No KV cache: the caller passes the whole sequence each step."""
+        n, S, _ = x.shape
+        self.begin_decoder_pass(False)
+        xf = self.llm.forward(x.to(self.device, BF16).contiguous(), key_mask.to(self.device).to(torch.uint8).contiguous(), save=False)
+        rows = (torch.arange(n, device=self.device, dtype=torch.int32) + 1) * S - 1
+        return ops.gemm(ops.gather_rows(xf, rows), self.llm.lm_head, out_f32=True)
+
     # ------------------------------------------------------------------ backward
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:
         """Backward of the last forward(train=True); grad_out is d(total)/d(loss) (device scalar, default 1)."""

@@ -250,8 +250,37 @@ class LlamaB200ForCausalLM(nn.Module):
             raise RuntimeError("LLM is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
         return self._step.llm_forward(inputs_embeds, attention_mask, labels)
 
-    def generate(self, *a, **kw):
-        raise NotImplementedError("generate() (beam-search decode path) is outside the training-step hot path (SURVEY.md §8f rank 4)")
+    @torch.no_grad()
+    def generate(self, inputs_embeds=None, attention_mask=None, max_new_tokens=200, num_beams=4, do_sample=False, min_length=1, top_p=1.0,
+                 repetition_penalty=1.0, length_penalty=1.0, temperature=1.0, bos_token_id=None, eos_token_id=None, pad_token_id=None, **kw):
+        """`llm.generate(inputs_embeds=..., ...)` as slam_model.generate calls it (slam_model.py:439-454): greedy / beam search / sampling control
+        flow in slam_llm_b200.generation (transformers v4.35.2 semantics), next-token logits from the B200 decoder.  No KV cache yet: every step
+        re-runs the decoder on prompt + generated tokens (decode is outside the training hot path)."""
+        from slam_llm_b200 import generation
+        if self._step is None:
+            raise RuntimeError("LLM is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
+        if inputs_embeds is None:
+            raise NotImplementedError("generate() is driven by inputs_embeds, as slam_model.generate does")
+        eng = self._step.b200
+        dev = eng.device
+        prompt = inputs_embeds.to(dev, torch.bfloat16)
+        B, S0, _ = prompt.shape
+        mask = torch.ones(B, S0, dtype=torch.uint8, device=dev) if attention_mask is None else attention_mask.to(dev).to(torch.uint8)
+        table = eng.llm.embed
+
+        def next_logits(tokens, beam_src):
+            n, t = tokens.shape
+            reps = n // B
+            x = prompt.repeat_interleave(reps, dim=0) if reps > 1 else prompt
+            m = mask.repeat_interleave(reps, dim=0) if reps > 1 else mask
+            if t > 0:
+                x = torch.cat([x, torch.nn.functional.embedding(tokens.to(dev), table)], dim=1)
+                m = torch.cat([m, torch.ones(n, t, dtype=torch.uint8, device=dev)], dim=1)
+            return eng.decoder_last_logits(x, m)
+
+        return generation.generate(next_logits, B, max_new_tokens=max_new_tokens, num_beams=num_beams, do_sample=do_sample, min_length=min_length,
+                                   top_p=top_p, repetition_penalty=repetition_penalty, length_penalty=length_penalty, temperature=temperature,
+                                   eos_token_id=eos_token_id, pad_token_id=pad_token_id).to(dev)
 
 
 def setup_llm(train_config, model_config, **kwargs):
@@ -530,6 +559,7 @@ class slam_model(nn.Module):
     def _inputs_embeds(self, batch):
         from slam_llm_b200 import ops
         dev = self.b200.device
+        self.b200.begin_decoder_pass(False)                         # deferred update / fp32 masters -> bf16 operands before anything reads them
         mel = batch.get("audio_mel")
         mel = self.b200.log_mel(batch["audio_pcm"].to(dev, torch.float32), batch.get("audio_pcm_lengths")) if mel is None else mel.to(dev, torch.float32)
         aud = self.b200.projector.forward(self.b200.encoder.forward(mel), save=False)
@@ -537,5 +567,18 @@ class slam_model(nn.Module):
                                self.b200.llm.embed)
 
     @torch.no_grad()
-    def generate(self, *a, **kw):
-        raise NotImplementedError("generate() (decode path) is outside the training-step hot path (SURVEY.md §8f rank 4)")
+    def generate(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
+                 output_attentions=None, output_hidden_states=None, return_dict=None, **kwargs):
+        """slam_model.py:409-456: inputs_embeds through forward(inference_mode=True), then llm.generate with the reference's defaults."""
+        kwargs["inference_mode"] = True
+        inputs_embeds, attention_mask = self.forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                                                     past_key_values=past_key_values, inputs_embeds=inputs_embeds, labels=labels, use_cache=use_cache,
+                                                     output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                                                     return_dict=return_dict, **kwargs)
+        tok = self.tokenizer
+        return self.llm.generate(inputs_embeds=inputs_embeds, max_new_tokens=kwargs.get("max_new_tokens", 200), num_beams=kwargs.get("num_beams", 4),
+                                 do_sample=kwargs.get("do_sample", False), min_length=kwargs.get("min_length", 1), top_p=kwargs.get("top_p", 1.0),
+                                 repetition_penalty=kwargs.get("repetition_penalty", 1.0), length_penalty=kwargs.get("length_penalty", 1.0),
+                                 temperature=kwargs.get("temperature", 1.0), attention_mask=attention_mask,
+                                 bos_token_id=getattr(tok, "bos_token_id", None), eos_token_id=getattr(tok, "eos_token_id", None),
+                                 pad_token_id=getattr(tok, "pad_token_id", None))
