@@ -79,3 +79,25 @@ def test_training_reduces_loss_and_checkpoint_roundtrip(tmp_path):
     # same trainables, but frozen weights are re-drawn from the same seeds in both builds -> identical eval loss
     assert abs(o1.loss.item() - o2.loss.item()) < 1e-3
     assert o1.logits is not None and o1.logits.shape[:2] == b["input_ids"].shape
+
+
+def test_inference_batch_decodes_a_test_split(tmp_path):
+    """pipeline/inference_batch.main (the entry of examples/asr_librispeech/inference_asr_batch.py): plugin model, jsonl dataset in
+    inference mode (left-padded [audio, prompt] + keys / targets), model.generate with the reference defaults, pred / gt files."""
+    import slam_llm  # noqa: F401
+    from recipe_util import make_data, make_llm_dir, run_config
+    from slam_llm.pipeline.inference_batch import main
+    llm_dir = make_llm_dir(str(tmp_path / "llm"))
+    jsonl = make_data(str(tmp_path / "data"), n=3)
+    out = str(tmp_path / "out")
+    os.makedirs(out, exist_ok=True)
+    cfg = run_config(llm_dir, jsonl, out, os.path.join(HERE, "recipe_model.py") + ":model_factory",
+                     os.path.join(ROOT, "src/slam_llm/datasets/speech_dataset.py") + ":get_speech_dataset", val_batch_size=2)
+    cfg.dataset_config.inference_mode = True
+    cfg.decode_log = os.path.join(out, "decode")
+    # (generation knobs are the reference defaults: the batch carries none, slam_model.py:441-449 -> 4 beams, up to 200 new tokens)
+    pred_path, gt_path = main(cfg)
+    pred = open(pred_path).read().strip().split("\n")
+    gt = open(gt_path).read().strip().split("\n")
+    assert len(pred) == len(gt) == 3 and all(line.split("\t")[0].startswith("utt") for line in pred)
+    assert [g.split("\t")[1] for g in gt] == ["hello world ", "hello world ab", "hello world abab"] or all("hello world" in g for g in gt)
