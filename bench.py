@@ -687,12 +687,17 @@ def run_ours(args):
             "gemm_time_share_of_step": round(gemm_ms / ms_instr, 4),
             "measured_over": f"{args.steps} instrumented steps (CUDA events around every GEMM launch) run right after the timed region", "step_algorithmic_tflop": round(fl["total"] / 1e12, 2),
             "step_achieved_tflops": round(fl["total"] / (ms_per_step / 1e3) / 1e12, 1)}
-    traffic_file = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(traffic_file):
+    # DRAM bytes per GEMM launch: from the committed ncu pass over one eager step of this workload (tools/profile_round2.sh ->
+    # tools/step_kernel_table.py); hardware counters cannot be read inside this process, so the number is per capture, not per run
+    for traffic_file, key in (("r02_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")), ("r01_gemm_traffic.json", ("dram_bytes_per_launch",))):
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            d = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
+            for k in key:
+                d = d[k]
+            roof["traffic"], roof["traffic_source"] = d, "profiles/" + traffic_file
+            break
         except Exception:
-            pass
+            continue
     recipe = None
     if world == 1 and wl["batch"] is not None and not args.skip_recipe:
         try:
