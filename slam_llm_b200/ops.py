@@ -273,8 +273,19 @@ def attn_bwd(q, k, v, out, lse, dout, *, causal: bool, scale: float, key_mask=No
 
 
 # ------------------------------------------------------------------------------------------- merge / decoder element-wise
+_DEBUG_CHECKS = os.environ.get("SLAM_DEBUG_CHECKS", "0") == "1"
+
+
 def embed_merge(ids, modality_mask, audio, embed, out=None):
+    """SLAM_DEBUG_CHECKS=1 adds the host-side validation the reference gets for free from torch indexing (costs a device sync): token ids must
+    be < vocab and the audio span of every row must fit the projector output — otherwise the kernel clamps the span / reads what it is given."""
     assert ids.dtype == torch.int64 and modality_mask.dtype == torch.uint8
+    if _DEBUG_CHECKS:
+        if int(ids.max()) >= embed.shape[0]:
+            raise IndexError(f"embed_merge: token id {int(ids.max())} >= vocabulary {embed.shape[0]}")
+        if int(modality_mask.sum(dim=1).max()) > audio.shape[1]:
+            raise ValueError(f"embed_merge: a modality span of {int(modality_mask.sum(dim=1).max())} positions exceeds the {audio.shape[1]} audio tokens "
+                             "the projector produced (fix_length_audio / modality_mask mismatch)")
     _req(audio, BF16, "embed_merge.audio"); _req(embed, BF16, "embed_merge.embed")
     B, S = ids.shape
     Ta, D = audio.shape[1], audio.shape[2]

@@ -95,6 +95,11 @@ def train(model, train_dataloader, eval_dataloader, tokenizer, optimizer, lr_sch
     best_val_loss, best_val_acc = float("inf"), 0.0
     dynamic = train_config.batching_strategy == "dynamic"
     raw_model = getattr(model, "module", model)
+    if train_config.get("use_fp16", False) and is_main:
+        logger.warning("train_config.use_fp16=true: the B200 step computes in bf16 with fp32 accumulation; no GradScaler is created (scale == 1)")
+    if train_config.get("run_test_during_validation", False):
+        raise NotImplementedError("train_config.run_test_during_validation: the in-loop model.inference(...) decode of the reference "
+                                  "(utils/train_utils.py:306-320) is not wired; decode with pipeline/inference_batch.py instead")
 
     for epoch in range(train_config.num_epochs):
         epoch_start_time = time.perf_counter()
