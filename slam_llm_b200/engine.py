@@ -626,8 +626,9 @@ class LlamaLoRAB200:
         return dx
 
     # ---------------------------------------------------------------------------------------- forward
-    def forward(self, x: torch.Tensor, key_mask: torch.Tensor, save: bool) -> torch.Tensor:
-        """x bf16 [B,S,D] (inputs_embeds), key_mask u8 [B,S] -> final normed hidden bf16 [B*S, D]."""
+    def forward(self, x: torch.Tensor, key_mask: torch.Tensor, save: bool, kv_out: Optional[list] = None) -> torch.Tensor:
+        """x bf16 [B,S,D] (inputs_embeds), key_mask u8 [B,S] -> final normed hidden bf16 [B*S, D].
+        kv_out (decode prefill): receives one (K [B,S,Hkv,dh], V [B,S,Hkv,dh]) pair of post-RoPE keys / values per layer."""
         cfg = self.cfg
         B, S, D = x.shape
         M = B * S
@@ -645,6 +646,8 @@ class LlamaLoRAB200:
             k = qkv[:, Dq: Dq + Dkv].view(B, S, Hkv, dh)
             v = qkv[:, Dq + Dkv:].view(B, S, Hkv, dh)
             attn, lse = ops.attn_fwd(q, k, v, causal=True, scale=scale, key_mask=key_mask, need_lse=save)
+            if kv_out is not None:
+                kv_out.append((k.contiguous(), v.contiguous()))
             attn2 = attn.view(M, Dq)
             x2, sv_o = self._lin_fwd(attn2, Lw["wo"], "o", li, residual=x)
             xn2, rstd2 = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=save)
@@ -664,6 +667,40 @@ class LlamaLoRAB200:
         xf, rstd_f = ops.rmsnorm_fwd(x, self.norm, cfg.eps, need_rstd=save)
         if save:
             self.saved = dict(layers=saved_layers, x_last=x, rstd_f=rstd_f, B=B, S=S, key_mask=key_mask)
+        return xf
+
+    # ---------------------------------------------------------------------------------------- decode (KV cache)
+    def decode_step(self, x: torch.Tensor, cache: list, key_mask: torch.Tensor, pos: int) -> torch.Tensor:
+        """One new token per sequence: x bf16 [n, D] (its embedding), cache = [(K, V)] per layer with K/V [n, t, Hkv, dh] (post-RoPE, grown in
+        place of the list), key_mask u8 [n, t + 1] over cached + new positions, pos = the new token's position (RoPE index).
+        Returns the final normed hidden bf16 [n, D].  Same kernels as the training forward: fused QKV(+LoRA) GEMM, RoPE, flash attention
+        (q_len 1 against the cache, non-causal + key mask), O / SwiGLU GEMMs."""
+        cfg = self.cfg
+        n = x.shape[0]
+        H, Hkv, dh, Dq, Dkv = cfg.heads, cfg.kv_heads, cfg.dh, cfg.dq, cfg.dkv
+        cos, sin = self.rope_tables(pos + 1)
+        cos_t, sin_t = cos[pos: pos + 1].contiguous(), sin[pos: pos + 1].contiguous()
+        scale = 1.0 / math.sqrt(dh)
+        _THIN_POOL.begin(x.device)
+        for li, Lw in enumerate(self.layers):
+            xn1, _ = ops.rmsnorm_fwd(x, Lw["ln1"], cfg.eps, need_rstd=False)
+            qkv, _ = self._lin_fwd(xn1, Lw["wqkv"], "qkv", li, bias=Lw["bqkv"])
+            ops.rope_(qkv[:, : Dq + Dkv], H + Hkv, dh, 1, cos_t, sin_t)                # every row sits at position `pos`
+            K, V = cache[li]
+            K = torch.cat([K, qkv[:, Dq: Dq + Dkv].reshape(n, 1, Hkv, dh)], dim=1)
+            V = torch.cat([V, qkv[:, Dq + Dkv:].reshape(n, 1, Hkv, dh)], dim=1)
+            cache[li] = (K, V)
+            attn, _ = ops.attn_fwd(qkv[:, :Dq].reshape(n, 1, H, dh).contiguous(), K, V, causal=False, scale=scale, key_mask=key_mask)
+            x2, _ = self._lin_fwd(attn.view(n, Dq), Lw["wo"], "o", li, residual=x)
+            xn2, _ = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=False)
+            if self.fuse_swiglu:
+                hmid = torch.empty((n, cfg.ffn), device=x.device, dtype=BF16)
+                ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid)
+            else:
+                gu, _ = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
+                hmid = ops.swiglu_fwd(gu)
+            x, _ = self._lin_fwd(hmid, Lw["wd"], "down", li, residual=x2)
+        xf, _ = ops.rmsnorm_fwd(x, self.norm, cfg.eps, need_rstd=False)
         return xf
 
     # ---------------------------------------------------------------------------------------- backward
@@ -881,6 +918,32 @@ class SlamStepB200:
         xf = self.llm.forward(x.to(self.device, BF16).contiguous(), key_mask.to(self.device).to(torch.uint8).contiguous(), save=False)
         rows = (torch.arange(n, device=self.device, dtype=torch.int32) + 1) * S - 1
         return ops.gemm(ops.gather_rows(xf, rows), self.llm.lm_head, out_f32=True)
+
+    def decode_prefill(self, x: torch.Tensor, key_mask: torch.Tensor):
+        """Prompt pass of a decode session: -> (next-token logits f32 [n, V], state).  state = dict(cache=[(K, V)] per layer, mask u8 [n, S])."""
+        n, S, _ = x.shape
+        self.begin_decoder_pass(False)
+        key_mask = key_mask.to(self.device).to(torch.uint8).contiguous()
+        cache: list = []
+        xf = self.llm.forward(x.to(self.device, BF16).contiguous(), key_mask, save=False, kv_out=cache)
+        rows = (torch.arange(n, device=self.device, dtype=torch.int32) + 1) * S - 1
+        logits = ops.gemm(ops.gather_rows(xf, rows), self.llm.lm_head, out_f32=True)
+        return logits, dict(cache=cache, mask=key_mask, pos=S)
+
+    def decode_next(self, tokens: torch.Tensor, state: dict, beam_src: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Feed one token per sequence (i64 [n]) -> next-token logits f32 [n, V]; the KV cache in `state` grows by one position.
+        beam_src (i64 [n]): row i continues the sequence that was row beam_src[i] of the previous call (beam re-ordering / expansion)."""
+        dev = self.device
+        if beam_src is not None:
+            idx = beam_src.to(dev)
+            state["cache"] = [(K.index_select(0, idx), V.index_select(0, idx)) for K, V in state["cache"]]
+            state["mask"] = state["mask"].index_select(0, idx)
+        n = tokens.shape[0]
+        state["mask"] = torch.cat([state["mask"], torch.ones(n, 1, dtype=torch.uint8, device=dev)], dim=1).contiguous()
+        x = torch.nn.functional.embedding(tokens.to(dev), self.llm.embed)
+        xf = self.llm.decode_step(x.contiguous(), state["cache"], state["mask"], state["pos"])
+        state["pos"] += 1
+        return ops.gemm(xf, self.llm.lm_head, out_f32=True)
 
     # ------------------------------------------------------------------ backward
     def backward(self, grad_out: Optional[torch.Tensor] = None) -> None:

@@ -254,8 +254,8 @@ class LlamaB200ForCausalLM(nn.Module):
     def generate(self, inputs_embeds=None, attention_mask=None, max_new_tokens=200, num_beams=4, do_sample=False, min_length=1, top_p=1.0,
                  repetition_penalty=1.0, length_penalty=1.0, temperature=1.0, bos_token_id=None, eos_token_id=None, pad_token_id=None, **kw):
         """`llm.generate(inputs_embeds=..., ...)` as slam_model.generate calls it (slam_model.py:439-454): greedy / beam search / sampling control
-        flow in slam_llm_b200.generation (transformers v4.35.2 semantics), next-token logits from the B200 decoder.  No KV cache yet: every step
-        re-runs the decoder on prompt + generated tokens (decode is outside the training hot path)."""
+        flow in slam_llm_b200.generation (transformers v4.35.2 semantics), next-token logits from the B200 decoder with a KV cache (prefill
+        once, then one token per sequence per step; beam re-ordering index-selects the cache rows)."""
         from slam_llm_b200 import generation
         if self._step is None:
             raise RuntimeError("LLM is not bound to a B200 step yet (construct slam_model first); no CPU fallback")
@@ -266,17 +266,30 @@ class LlamaB200ForCausalLM(nn.Module):
         prompt = inputs_embeds.to(dev, torch.bfloat16)
         B, S0, _ = prompt.shape
         mask = torch.ones(B, S0, dtype=torch.uint8, device=dev) if attention_mask is None else attention_mask.to(dev).to(torch.uint8)
-        table = eng.llm.embed
+        session = {}
 
         def next_logits(tokens, beam_src):
+            """KV-cache decode: the prompt is run once (prefill, expanded to one copy per beam on the first beam step), afterwards each call feeds
+            the newest token of every sequence; beam_src re-orders the cache rows.  SLAM_DECODE_NO_CACHE=1 re-runs the whole sequence instead."""
             n, t = tokens.shape
             reps = n // B
-            x = prompt.repeat_interleave(reps, dim=0) if reps > 1 else prompt
-            m = mask.repeat_interleave(reps, dim=0) if reps > 1 else mask
-            if t > 0:
-                x = torch.cat([x, torch.nn.functional.embedding(tokens.to(dev), table)], dim=1)
-                m = torch.cat([m, torch.ones(n, t, dtype=torch.uint8, device=dev)], dim=1)
-            return eng.decoder_last_logits(x, m)
+            if os.environ.get("SLAM_DECODE_NO_CACHE", "0") == "1":
+                x = prompt.repeat_interleave(reps, dim=0) if reps > 1 else prompt
+                m = mask.repeat_interleave(reps, dim=0) if reps > 1 else mask
+                if t > 0:
+                    x = torch.cat([x, torch.nn.functional.embedding(tokens.to(dev), eng.llm.embed)], dim=1)
+                    m = torch.cat([m, torch.ones(n, t, dtype=torch.uint8, device=dev)], dim=1)
+                return eng.decoder_last_logits(x, m)
+            if t == 0:
+                logits, session["state"] = eng.decode_prefill(prompt, mask)
+                if reps > 1:                                   # beams start as copies of the prompt (their scores differ, not their state)
+                    rep = torch.arange(B, device=dev).repeat_interleave(reps)
+                    st = session["state"]
+                    st["cache"] = [(K.index_select(0, rep), V.index_select(0, rep)) for K, V in st["cache"]]
+                    st["mask"] = st["mask"].index_select(0, rep)
+                    logits = logits.index_select(0, rep)
+                return logits
+            return eng.decode_next(tokens[:, -1], session["state"], beam_src)
 
         return generation.generate(next_logits, B, max_new_tokens=max_new_tokens, num_beams=num_beams, do_sample=do_sample, min_length=min_length,
                                    top_p=top_p, repetition_penalty=repetition_penalty, length_penalty=length_penalty, temperature=temperature,

@@ -25,8 +25,14 @@ def _oracle_next_logits(om, prompt, mask):
 
 
 @pytest.mark.parametrize("kw", [dict(num_beams=1, max_new_tokens=10), dict(num_beams=4, max_new_tokens=10),
-                                dict(num_beams=3, max_new_tokens=8, repetition_penalty=1.2, length_penalty=0.7, min_length=3)])
-def test_generate_matches_oracle_decoding(tmp_path, kw):
+                                dict(num_beams=3, max_new_tokens=8, repetition_penalty=1.2, length_penalty=0.7, min_length=3),
+                                dict(num_beams=4, max_new_tokens=10, no_cache=True)])
+def test_generate_matches_oracle_decoding(tmp_path, kw, monkeypatch):
+    kw = dict(kw)
+    if kw.pop("no_cache", False):                       # the cache-less path (whole sequence re-run every step) must give the same tokens
+        monkeypatch.setenv("SLAM_DECODE_NO_CACHE", "1")
+    else:
+        monkeypatch.delenv("SLAM_DECODE_NO_CACHE", raising=False)
     import slam_llm  # noqa: F401
     from omegaconf import OmegaConf
     from slam_llm.models.slam_model import model_factory
