@@ -74,6 +74,8 @@ def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 64 else 1)
     nkb = (K + 63) // 64 + ((a2.shape[1] + 63) // 64 if a2 is not None else 0)
     split = min(8, nkb // 4, max(1, 148 // tiles))
+    if nkb < 128:      # measured (tools/thin_probe.py, M=1604 N=64): K=4096 16.5 us unsplit vs 22.8 us split-8 + cast; K=6144 22.4 vs 23.8; K=14336 46.1 vs 26.9
+        split = 1
     if split <= 1:
         return ops.gemm(a, b, a2=a2, b2=b2)
     return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out=_THIN_POOL.take(M, N, a.device), out_f32=True, split_k=split))
