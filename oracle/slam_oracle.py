@@ -17,11 +17,14 @@ It restates, in plain PyTorch fp32/fp64 on the CPU, the arithmetic the reference
 
 openai-whisper, transformers==4.35.2 and peft==0.6.0 are third-party dependencies that are NOT vendored
 under /root/reference; their published algorithms are restated here from formula.
-PINNING: the reference's own tests hold no golden vector for this path ("parity unpinned" by the
-reference).  This oracle is pinned instead against the installed transformers 5.5.0
-implementations of the same third-party arithmetic (WhisperFeatureExtractor, WhisperEncoder layers,
-LlamaForCausalLM eager attention + loss) in tests/test_oracle_pinning.py, and committed golden vectors
-generated from it live in tests/golden/ (generator: tests/golden/make_golden.py).
+PINNING (round 2): the reference's own tests hold no golden vector for this path, so the oracle is pinned to
+OUTPUTS OF THE REFERENCE ITSELF RUN IN THE BUILD CONTAINER: tests/golden/make_ref_golden.py imports /root/reference/src/slam_llm unmodified
+(through tests/ref_glue.py's stand-ins for the absent peft / openai-whisper / kaldiio packages), runs its datasets + collators,
+setup_encoder / setup_llm / setup_encoder_projector, slam_model.forward (and examples/s2s/model/slam_model_s2s.py), backward and
+torch.optim.AdamW on the CPU and commits the results as tests/golden/ref_*.pt; tests/test_ref_pinning.py requires this oracle to
+reproduce them at fp32 level (loss 1e-5, activations 1e-4, gradients 1e-4), including Whisper-large-v3 / Llama-3-8B widths at depth 1.
+The third-party arithmetic is additionally pinned to the installed transformers 5.5.0 modules (WhisperFeatureExtractor, WhisperEncoder
+layers, LlamaForCausalLM / Qwen2ForCausalLM eager attention + loss) in tests/test_oracle_pinning.py.
 """
 from __future__ import annotations
 
