@@ -487,13 +487,16 @@ class OracleModel:
     def forward(self, batch: Dict[str, torch.Tensor], return_all: bool = False, lora_masks=None):
         """batch keys as produced by SpeechDatasetJsonl.collator (speech_dataset.py:216-291); audio either as
         `audio_mel` [B,T,n_mels] or raw `audio_pcm` [B,n] (log-mel computed here)."""
-        mel = batch.get("audio_mel")
-        if mel is None:
-            mel = batch_log_mel(batch["audio_pcm"], self.enc_cfg.n_mels, batch.get("audio_pcm_lengths"))
         dtype = self.llm_w["model.embed_tokens.weight"].dtype
-        mel = mel.to(dtype)
-        with torch.no_grad():                                            # encoder frozen (slam_model.py:110-113)
-            enc = whisper_encoder(self.enc_w, self.enc_cfg, mel)
+        if "encoder_out" in batch:                                       # a non-Whisper (foreign, frozen) encoder produced the features
+            mel, enc = None, batch["encoder_out"].to(dtype)
+        else:
+            mel = batch.get("audio_mel")
+            if mel is None:
+                mel = batch_log_mel(batch["audio_pcm"], self.enc_cfg.n_mels, batch.get("audio_pcm_lengths"))
+            mel = mel.to(dtype)
+            with torch.no_grad():                                        # encoder frozen (slam_model.py:110-113)
+                enc = whisper_encoder(self.enc_w, self.enc_cfg, mel)
         aud = projector(self.proj_w, self.proj_cfg, enc)
         x = merge(self.llm_w["model.embed_tokens.weight"], batch["input_ids"], batch["modality_mask"].bool(), aud)
         logits = llama_forward(self.llm_w, self.lora_w, self.llm_cfg, self.lora_cfg, x, batch["attention_mask"], lora_masks=lora_masks)

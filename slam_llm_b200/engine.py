@@ -782,17 +782,21 @@ class SlamStepB200:
         self._assemble(encoder, projector, llm, arena, device)
 
     @classmethod
-    def from_parts(cls, encoder: WhisperEncoderB200, projector: ProjectorB200, llm: LlamaLoRAB200, arena: TrainableArena, device) -> "SlamStepB200":
-        """Assemble a step from already-built components sharing one (finalized) arena (used by the slam_llm mirror)."""
+    def from_parts(cls, encoder: Optional[WhisperEncoderB200], projector: ProjectorB200, llm: LlamaLoRAB200, arena: TrainableArena, device,
+                   enc_cfg: Optional[EncoderCfg] = None) -> "SlamStepB200":
+        """Assemble a step from already-built components sharing one (finalized) arena (used by the slam_llm mirror).
+        encoder=None: the modality encoder is a foreign (frozen, torch) module run by the caller, who enters at forward_rest() with its output;
+        enc_cfg then only carries the feature width `d`."""
         self = cls.__new__(cls)
-        self._assemble(encoder, projector, llm, arena, _require_cuda(device))
+        self._assemble(encoder, projector, llm, arena, _require_cuda(device), enc_cfg)
         return self
 
-    def _assemble(self, encoder, projector, llm, arena, device) -> None:
+    def _assemble(self, encoder, projector, llm, arena, device, enc_cfg=None) -> None:
         self.device = device
-        self.enc_cfg, self.llm_cfg, self.lora_cfg, self.proj_cfg = encoder.cfg, llm.cfg, llm.lora, projector.cfg
+        self.enc_cfg = encoder.cfg if encoder is not None else enc_cfg
+        self.llm_cfg, self.lora_cfg, self.proj_cfg = llm.cfg, llm.lora, projector.cfg
         self.arena, self.encoder, self.projector, self.llm = arena, encoder, projector, llm
-        self.filters_t = mel_filterbank(self.enc_cfg.n_mels).t().contiguous().to(device)
+        self.filters_t = mel_filterbank(self.enc_cfg.n_mels).t().contiguous().to(device) if encoder is not None else None
         self._ctx = None
         self.micro_steps = 0   # backward() calls since the last optimizer step (gradient accumulation)
         self.lora_dropout_enabled = True   # module.train()/eval() of the host mirror toggles this (reference quirk Q6)
@@ -855,6 +859,8 @@ class SlamStepB200:
     def forward_front(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """log-mel (unless the batch carries audio_mel) + Whisper encoder: the part of the step that is independent of the trainables."""
         dev = self.device
+        if self.encoder is None:
+            raise RuntimeError("this step has no B200 encoder (foreign modality encoder): run it yourself and enter at forward_rest(batch, enc_out)")
         mel = batch.get("audio_mel")
         if mel is None:
             mel = self.log_mel(batch["audio_pcm"].to(dev, F32), batch.get("audio_pcm_lengths"))

@@ -118,3 +118,45 @@ class WhisperWrappedEncoder:
             logger.warning(f"encoder_path={path!r} is not a file: RANDOM-INIT Whisper encoder with dims {cfg} (b200_random_init)")
             eng = WhisperEncoderB200(cfg, None, device)
         return WhisperEncoderModule(eng)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Non-Whisper ("foreign") modality encoders: frozen torch modules that the user's environment provides (fairseq EAT, BEATs, WavLM, ...).
+# They run as they are (torch, no B200 kernels: their networks live in un-vendored third-party code); everything that trains -
+# projector, merge, decoder, loss, optimizer - runs on the B200 step, which is entered with their output (SlamStepB200.forward_rest).
+# ---------------------------------------------------------------------------------------------------------------------
+_FOREIGN = {}
+
+
+def register_encoder(name: str, loader, call) -> None:
+    """loader(model_config) -> nn.Module;  call(module, batch_kwargs) -> features [B, T, encoder_dim] (what slam_model.forward computes for
+    this `model_config.encoder_name`, models/slam_model.py:319-353)."""
+    _FOREIGN[name] = (loader, call)
+
+
+def foreign_encoder(name: str):
+    return _FOREIGN.get(name)
+
+
+class EATEncoder:
+    """models/encoder.py:65-78: the EAT network is fairseq user code (`model_config.encoder_fairseq_dir`), loaded exactly like the reference."""
+
+    @classmethod
+    def load(cls, model_config):
+        try:
+            import fairseq
+        except ImportError as e:
+            raise ImportError("encoder_name=eat needs `fairseq` and the EAT user directory (model_config.encoder_fairseq_dir), as in the reference; "
+                              "neither ships with this package") from e
+        from dataclasses import dataclass
+
+        @dataclass
+        class UserDirModule:
+            user_dir: str
+        fairseq.utils.import_user_module(UserDirModule(model_config.encoder_fairseq_dir))
+        models, _, _ = fairseq.checkpoint_utils.load_model_ensemble_and_task([model_config.encoder_path])
+        return models[0]
+
+
+register_encoder("eat", EATEncoder.load,
+                 lambda enc, kw: enc.model.extract_features(kw["audio_mel"].unsqueeze(dim=1), padding_mask=None, mask=False, remove_extra_tokens=False)["x"])

@@ -62,9 +62,23 @@ def setup_encoder(train_config, model_config, **kwargs):
     if len(encoder_list) == 0:
         return None
     encoder_name = encoder_list[0]
+    from slam_llm.models.encoder import WhisperWrappedEncoder, foreign_encoder
+    if len(encoder_list) == 1 and foreign_encoder(encoder_name) is not None:
+        # a frozen torch encoder from the user's environment (EAT via fairseq, or anything added with register_encoder): it runs as it is,
+        # the B200 step takes over at its output (projector, merge, decoder, loss, optimizer)
+        if not train_config.freeze_encoder:
+            raise NotImplementedError("freeze_encoder=false: foreign encoders are run frozen (no gradient reaches them)")
+        encoder = foreign_encoder(encoder_name)[0](model_config)
+        for _, param in encoder.named_parameters():
+            param.requires_grad = False
+        encoder.eval()
+        if torch.cuda.is_available():
+            encoder.to(torch.device("cuda", torch.cuda.current_device()))
+        print_module_size(encoder, encoder_name, _rank(train_config))
+        return encoder
     if len(encoder_list) != 1 or encoder_name not in ("whisper", "qwen-audio"):
-        raise NotImplementedError(f"encoder_name={model_config.encoder_name!r}: only the Whisper encoder is on the B200 path (SURVEY.md §2.1)")
-    from slam_llm.models.encoder import WhisperWrappedEncoder
+        raise NotImplementedError(f"encoder_name={model_config.encoder_name!r}: built in are the Whisper encoder (B200 kernels) and EAT (fairseq, foreign); "
+                                  "other frozen torch encoders can be plugged in with slam_llm.models.encoder.register_encoder")
     encoder = WhisperWrappedEncoder.load(model_config)
     print_module_size(encoder, encoder_name, _rank(train_config))
     if train_config.freeze_encoder:
@@ -438,7 +452,18 @@ class slam_model(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device())
         arena = TrainableArena()
         proj_cfg = ProjCfg(encoder_projector.kind, encoder_projector.k, encoder_projector.linear1.out_features)
-        eng_proj = ProjectorB200(encoder.b200.cfg, llm.cfg, proj_cfg, arena)
+        self._foreign_call = None
+        if getattr(encoder, "b200", None) is None:                  # frozen torch encoder (slam_llm.models.encoder.register_encoder)
+            from slam_llm.models.encoder import foreign_encoder
+            from slam_llm_b200.config import EncoderCfg
+            entry = foreign_encoder(model_config.encoder_name)
+            if entry is None:
+                raise NotImplementedError(f"encoder of type {type(encoder).__name__} is neither the B200 Whisper encoder nor a registered foreign encoder")
+            self._foreign_call = entry[1]
+            enc_cfg = EncoderCfg(n_mels=0, n_ctx=0, d=int(model_config.encoder_dim), heads=1, layers=0)
+        else:
+            enc_cfg = encoder.b200.cfg
+        eng_proj = ProjectorB200(enc_cfg, llm.cfg, proj_cfg, arena)
         seed = int(train_config.get("seed", 42))                    # adapters + LoRA dropout follow train_config.seed like the reference's global RNG
         llm.bind(arena, device, seed=seed)
         arena.finalize(device)
@@ -454,7 +479,7 @@ class slam_model(nn.Module):
                 raise KeyError(f"peft_ckpt holds adapters this model does not have: {unknown[:4]} ...")
             for k, v in sd.items():
                 mine[k].copy_(v.to(device, torch.float32))
-        self.b200 = SlamStepB200.from_parts(encoder.b200, eng_proj, llm.b200, arena, device)
+        self.b200 = SlamStepB200.from_parts(getattr(encoder, "b200", None), eng_proj, llm.b200, arena, device, enc_cfg=enc_cfg)
         object.__setattr__(llm, "_step", self)       # plain attribute: registering the parent as a sub-module would create a cycle
         object.__setattr__(encoder_projector, "_step", self.b200)
         arena.param.requires_grad_(True)
@@ -544,6 +569,8 @@ class slam_model(nn.Module):
         audio_mel = kwargs.get("audio_mel", None)
         audio_pcm = kwargs.get("audio_pcm", None)
         modality_mask = kwargs.get("modality_mask", None)
+        if self._foreign_call is not None:
+            return self._forward_foreign(input_ids, attention_mask, labels, modality_mask, kwargs)
         if audio_mel is None and audio_pcm is None:
             raise NotImplementedError("the B200 step needs audio_mel or audio_pcm in the batch (Whisper recipes)")
         if self.train_config.freeze_encoder:
@@ -568,6 +595,31 @@ class slam_model(nn.Module):
         if not self.metric:
             acc = -1
         return outputs, acc
+
+    def _forward_foreign(self, input_ids, attention_mask, labels, modality_mask, kwargs):
+        """slam_model.py:314-407 with a frozen torch encoder: its features (computed here, no grad) enter the B200 step at the projector."""
+        eng = self.b200
+        self.encoder.eval()
+        with torch.no_grad():
+            feats = self._foreign_call(self.encoder, {k: (v.to(eng.device) if torch.is_tensor(v) else v) for k, v in kwargs.items()})
+        feats = feats.to(eng.device, torch.bfloat16).contiguous()
+        batch = dict(input_ids=input_ids, labels=labels, attention_mask=attention_mask, modality_mask=modality_mask)
+        for k in ("_rows", "_targets"):
+            if kwargs.get(k, None) is not None:
+                batch[k] = kwargs[k]
+        if kwargs.get("inference_mode", False):
+            from slam_llm_b200 import ops
+            eng.begin_decoder_pass(False)
+            aud = eng.projector.forward(feats, save=False)
+            return ops.embed_merge(input_ids.to(eng.device).contiguous(), modality_mask.to(eng.device).to(torch.uint8).contiguous(), aud, eng.llm.embed), attention_mask
+        train = torch.is_grad_enabled() and labels is not None
+        eng.lora_dropout_enabled = self.training
+        full = (not train) or bool(self.train_config.get("b200_full_logits", False))
+        eng.flush_update()
+        loss, acc, logits = eng.forward_rest(batch, feats, train=train, full_logits=full)
+        if train:
+            loss = _StepLoss.apply(eng.arena.param, loss, self)
+        return _Outputs(loss=loss, logits=logits), (acc if self.metric else -1)
 
     def _inputs_embeds(self, batch):
         from slam_llm_b200 import ops

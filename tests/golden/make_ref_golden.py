@@ -361,6 +361,44 @@ def collator_cases() -> dict:
     return dict(samples=samples, collated={k: v for k, v in out.items() if v is not None})
 
 
+def audio_dataset_case() -> dict:
+    """The reference's datasets/audio_dataset.py (EAT front end: models/EAT/EAT.py EAT_preprocess + item layout + collator) on fabricated WAVs."""
+    import importlib
+    ref_glue.install()
+    mod = importlib.import_module("slam_llm.datasets.audio_dataset")
+    assert mod.__file__.startswith(ref_glue.REFERENCE_SRC)
+
+    def _wav_load(path, *a, **kw):
+        """torchaudio.load needs torchcodec in torchaudio 2.11 (absent offline): 16-bit PCM WAV through scipy, same return convention
+        ([channels, n] float32 in [-1, 1), sample rate)."""
+        from scipy.io import wavfile
+        rate, data = wavfile.read(path)
+        return torch.from_numpy(data.astype("float32") / 32768.0).reshape(1, -1), rate
+    mod.torchaudio.load = _wav_load
+    tok = ref_glue.CharTokenizer(1000)
+    g = torch.Generator().manual_seed(77)
+    pcm, samples = [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        rows = []
+        for i, (secs, target) in enumerate(((1.234, "a dog barks"), (2.5, "rain"), (0.8, "birds are singing loudly"))):
+            p = (torch.randn(int(secs * 16000), generator=g) * 0.1 * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+            pcm.append(p)
+            wav = os.path.join(tmp, f"aac{i}.wav")
+            ref_glue.write_wav(wav, p.numpy())
+            rows.append({"key": f"aac{i}", "source": wav, "target": target})
+        jl = os.path.join(tmp, "aac.jsonl")
+        with open(jl, "w") as f:
+            f.write("\n".join(json.dumps(r) for r in rows))
+        dc = OmegaConf.create(dict(train_data_path=jl, val_data_path=jl, prompt="Describe the audio you hear.", fix_length_audio=-1, input_type="mel",
+                                   model_name="eat", fbank_mean=-4.268, fbank_std=4.569, target_length=1024, fixed_length=False, random_crop=False,
+                                   encoder_projector_ds_rate=5, inference_mode=False))
+        ds = mod.get_audio_dataset(dc, tok, "train")
+        samples = [ds[i] for i in range(len(ds))]
+        batch = ds.collator(samples)
+    return dict(pcm_int16=pcm, items=[{k: v for k, v in s.items() if torch.is_tensor(v) or isinstance(v, (int, str))} for s in samples],
+                collated={k: v for k, v in batch.items() if torch.is_tensor(v)})
+
+
 def _cmp(a, b, path=""):
     if isinstance(a, dict):
         assert set(a) == set(b), (path, set(a) ^ set(b))
@@ -389,6 +427,7 @@ def main():
     todo = {f"ref_{c}.pt": (lambda c=c: reference_step(c)) for c in CASES}
     todo["ref_collator.pt"] = collator_cases
     todo["ref_s2s.pt"] = reference_s2s_step
+    todo["ref_audio_dataset.pt"] = audio_dataset_case
     for name, fn in todo.items():
         if args.only and args.only not in name:
             continue

@@ -174,8 +174,8 @@ def test_dynamic_dataset_mirror_reproduces_the_reference_batches(tmp_path):
     import json
     import numpy as np
     from scipy.io import wavfile
-    from omegaconf import OmegaConf
     from slam_llm.datasets.speech_dataset_large import get_speech_dataset
+    from omegaconf import OmegaConf
     from ref_glue import CharTokenizer
     fix = rf.load("ref_tiny_dynamic.pt")
     dyn = fix["dynamic"]
@@ -205,11 +205,46 @@ def test_dynamic_dataset_mirror_reproduces_the_reference_batches(tmp_path):
     assert picked["audio_pcm"].shape[1] // 160 == fix["mel_frames"]
 
 
+def test_audio_dataset_mirror_matches_the_reference_audio_dataset(tmp_path):
+    """src/slam_llm/datasets/audio_dataset.py (EAT front end + item layout + collator; the aac_audiocaps recipes) vs what the reference's
+    datasets/audio_dataset.py produced on the same WAV files (tests/golden/ref_audio_dataset.pt)."""
+    import json
+    import numpy as np
+    from scipy.io import wavfile
+    from slam_llm.datasets.audio_dataset import get_audio_dataset       # (importing slam_llm installs the omegaconf shim when needed)
+    from omegaconf import OmegaConf
+    from ref_glue import CharTokenizer
+    fix = rf.load("ref_audio_dataset.pt")
+    rows = []
+    for i, (p, target) in enumerate(zip(fix["pcm_int16"], ("a dog barks", "rain", "birds are singing loudly"))):
+        wav = str(tmp_path / f"a{i}.wav")
+        wavfile.write(wav, 16000, p.numpy().astype(np.int16))
+        rows.append({"key": f"aac{i}", "source": wav, "target": target})
+    jl = tmp_path / "aac.jsonl"
+    jl.write_text("\n".join(json.dumps(r) for r in rows))
+    dc = OmegaConf.create(dict(train_data_path=str(jl), val_data_path=str(jl), prompt="Describe the audio you hear.", fix_length_audio=-1, input_type="mel",
+                               model_name="eat", fbank_mean=-4.268, fbank_std=4.569, target_length=1024, fixed_length=False, random_crop=False,
+                               encoder_projector_ds_rate=5, inference_mode=False))
+    ds = get_audio_dataset(dc, CharTokenizer(1000), "train")
+    items = [ds[i] for i in range(len(ds))]
+    for got, want in zip(items, fix["items"]):
+        assert got["audio_length"] == want["audio_length"] and got["target"] == want["target"]
+        for k in ("input_ids", "labels", "attention_mask"):
+            assert torch.equal(got[k], want[k]), k
+        assert got["audio_mel"].shape == want["audio_mel"].shape and (got["audio_mel"] - want["audio_mel"]).abs().max().item() < 1e-5
+    batch = ds.collator(items)
+    for k, v in fix["collated"].items():
+        if v.is_floating_point():
+            assert (batch[k].float() - v.float()).abs().max().item() < 1e-5, k
+        else:
+            assert torch.equal(batch[k].to(v.dtype), v), k
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/slam_llm"), reason="/root/reference is only present in the build container")
 def test_fixtures_regenerate_from_the_reference_code():
     """Re-run the reference's own code (dedicated process: its `slam_llm` package shadows this repo's mirror) and compare with the
     committed fixtures.  The real-width case is left to `make_ref_golden.py --check --only realwidth` (3 min)."""
-    for only in ("tiny", "collator", "s2s"):   # "tiny" matches ref_tiny, ref_tiny_cov1d_all and ref_tiny_dynamic
+    for only in ("tiny", "collator", "s2s", "audio_dataset"):   # "tiny" matches ref_tiny, ref_tiny_cov1d_all and ref_tiny_dynamic
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_ref_golden.py"), "--check", "--only", only],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
