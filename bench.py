@@ -334,7 +334,7 @@ class _SyntheticUtterances(torch.utils.data.Dataset):
         return self._collator.collator(samples)
 
 
-def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup):
+def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup, rank=0, local_rank=0, world=1):
     """`e2e_recipe`: slam_llm.utils.train_utils.train() (the reference's loop, utils/train_utils.py:46-392) over a DataLoader (2 workers, pinned
     memory) of FRESH synthetic batches: collate, H2D, label rows, model(**batch), outputs.loss.backward(), FlatAdamW.step(), LambdaLR.step(), the
     per-step tqdm description (one D2H read per step).  Wall-clock around the whole epoch of `steps` batches, device synchronised on both sides."""
@@ -342,10 +342,14 @@ def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup):
     from slam_llm.utils.train_utils import train
     from slam_llm_b200.optim import FlatAdamW
     log_config = OmegaConf.create(dict(use_wandb=False, log_interval=10))
+    if world > 1:                                                  # what pipeline/finetune.py sets up for enable_ddp (finetune.py:84-90 of the mirror)
+        train_config.enable_ddp = True
+        model.ddp_world_size = world
+        model.b200.defer_update = True
     optimizer = FlatAdamW(model, lr=train_config.lr, weight_decay=train_config.weight_decay)
     scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda step: min((step + 1) / train_config.warmup_steps, 1))
 
-    ds = _SyntheticUtterances(wl, llm.vocab, steps * wl["batch"], seed=2)
+    ds = _SyntheticUtterances(wl, llm.vocab, steps * wl["batch"], seed=2 + rank)
     dl = torch.utils.data.DataLoader(ds, batch_size=wl["batch"], num_workers=2, pin_memory=True, collate_fn=ds.collator, drop_last=True,
                                      persistent_workers=True, prefetch_factor=4)
 
@@ -369,7 +373,8 @@ def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup):
         st = _Stamped(dl)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = train(model, st, None, None, optimizer, scheduler, 1, train_config, log_config)
+        res = train(model, st, None, None, optimizer, scheduler, 1, train_config, log_config, None, local_rank if world > 1 else None,
+                    rank if world > 1 else None)
         model.b200.flush_update()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -380,8 +385,13 @@ def recipe_leg(wl, model, train_config, llm, audio_s, steps, warmup):
     t_first, _, _ = epoch()                                       # warm-up epoch: also pays the DataLoader worker start-up (fork + first prefetch)
     t, steady, res = epoch()                                      # timed epoch: the same persistent workers, `steps` fresh batches
     del dl
+    if world > 1:                                                 # slowest rank decides
+        tt = torch.tensor([steady, t], device=model.b200.device, dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        steady, t = float(tt[0]), float(tt[1])
+        train_config.enable_ddp = False
     ms = steady * 1e3
-    return {"value": round(audio_s / (ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
+    return {"value": round(world * audio_s / (ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
             "whole_epoch_ms_per_step": round(t * 1e3 / steps, 3), "first_epoch_ms_per_step": round(t_first * 1e3 / steps, 3),
             "measured": "steady state of the timed epoch: wall clock from the hand-over of batch 5 to the hand-over of batch K (train() reads the loss "
                         "on the host every step, so hand-overs are step boundaries); whole_epoch also pays MemoryTrace's per-epoch gc + empty_cache "
@@ -685,6 +695,13 @@ def run_ours(args):
 
     if args.breakdown:
         scale_breakdown(args, eng, dev_batch, lr, rank, world, dev)
+    recipe = None
+    if wl["batch"] is not None and not args.skip_recipe:          # every rank: the recipe loop under DDP is a collective affair
+        try:
+            recipe = recipe_leg(wl, model, train_config, llm, audio_s, args.steps, args.warmup, rank, local_rank, world)
+        except Exception as e:
+            recipe = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        eng.defer_update = world > 1 and args.overlap == 1
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -709,12 +726,6 @@ def run_ours(args):
             break
         except Exception:
             continue
-    recipe = None
-    if world == 1 and wl["batch"] is not None and not args.skip_recipe:
-        try:
-            recipe = recipe_leg(wl, model, train_config, llm, audio_s, args.steps, args.warmup)
-        except Exception as e:
-            recipe = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     eager = None
     if world == 1 and not args.skip_eager and wl["batch"] is not None:
         eager = eager_baseline(wl, enc, llm, lora, host_batch, dev, eng, audio_s, e2e_value, model=model)
