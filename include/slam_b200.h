@@ -68,7 +68,11 @@ typedef struct slam_gemm_args {
                                      activation / residual, bf16 or f32 out) still applies */
   int64_t workspace_bytes;
   int32_t tail_split;             /* 0 = automatic (when a workspace is given), -1 = never, n > 1 = at most n k-slices per tile */
-  int32_t reserved;
+  int32_t transpose_out;          /* 0: out[M,N] as above.  1 ("swap-AB"): `out` and `residual` are the TRANSPOSED matrices, bf16 [N,M] with row
+                                     strides ldo / ldr: out[n][m] = sum_k A[m,k] B[n,k] (+ A2 B2) + residual[n][m].  The caller passes the WEIGHT
+                                     as A (rows a multiple of 256: no padding in a CTA-pair tile) and the activations as B, so the token
+                                     dimension becomes the flexible-width N of the tile and the result still lands as [tokens, features].
+                                     Needs bf16 out, act 0, no bias, no split_k */
   void* aux; int64_t ld_aux;      /* fused SwiGLU (HF LlamaMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x)), modeling_llama.py), with the
                                      gate/up pair stored "blocked-64": feature 64 b + i has its gate in column 128 b + i and its up in
                                      column 128 b + 64 + i of a [M, 2F] matrix (weights pre-permuted by the caller to match).

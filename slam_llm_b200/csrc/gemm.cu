@@ -382,6 +382,7 @@ static void fill_kparams(const slam_gemm_args* g, int block_m, int block_n, Gemm
   p.aux = reinterpret_cast<bf16*>(g->aux);
   p.ld_aux = g->ld_aux;
   p.alpha = g->alpha;
+  p.transpose_out = g->transpose_out != 0 ? 1 : 0;
   p.ksplit = g->split_k > 1 ? g->split_k : 1;
   const int nkb_total = p.kb1 + p.kb2;
   if (p.ksplit > nkb_total) p.ksplit = nkb_total;
@@ -585,9 +586,9 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   SLAM_CHECK_ARG(g != nullptr, "gemm: null args");
   SLAM_CHECK_ARG(g->m > 0 && g->n > 0 && g->k1 > 0, "gemm: bad shape m=%d n=%d k1=%d", g->m, g->n, g->k1);
   SLAM_CHECK_ARG(g->n % 8 == 0, "gemm: n=%d must be a multiple of 8", g->n);
-  SLAM_CHECK_ARG(g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
+  SLAM_CHECK_ARG(g->transpose_out != 0 || (g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0),
                  "gemm: output must be 16-byte aligned with ldo %% 8 == 0");
-  SLAM_CHECK_ARG(g->residual == nullptr || (g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0),
+  SLAM_CHECK_ARG(g->residual == nullptr || g->transpose_out != 0 || (g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0),
                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
   SLAM_CHECK_ARG(g->bias == nullptr || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
@@ -600,6 +601,8 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
                    "gemm: fused SwiGLU needs a 16-byte aligned aux, a bf16 output and no bias/residual/split_k");
     SLAM_CHECK_ARG(g->act == 3 ? g->n % 128 == 0 : g->n % 64 == 0, "gemm: fused SwiGLU needs whole blocked-64 groups (n=%d)", g->n);
   }
+  SLAM_CHECK_ARG(g->transpose_out == 0 || (!g->out_f32 && g->act == 0 && g->bias == nullptr && g->split_k <= 1),
+                 "gemm: transpose_out needs a bf16 output and no bias / activation / split_k");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
   if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1 && g->act < 3, g->split_k <= 1, g->act == 3, g->act == 4);

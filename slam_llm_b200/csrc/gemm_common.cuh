@@ -29,6 +29,9 @@ struct GemmKParams {
   bf16* aux;                  // fused SwiGLU: act 3 -> h [M, N/2] (written); act 4 -> gu [M, 2N] (read)
   long long ld_aux;
   float alpha;
+  int transpose_out;          // 1: the tile is C^T of the logical output: element (row r, col c) of the accumulator goes to out[c * ldo + r] (bf16),
+                              //    the residual is read the same way.  Lets the WEIGHT be the 256-row M operand of a CTA pair (rows % 256 == 0,
+                              //    no tile padding) while the token dimension becomes the flexible-width N (swap-AB, what cuBLAS does for M = 1604).
 };
 
 // One unit of work of a persistent CTA: k-blocks [kb_begin, kb_end) of one output tile.
@@ -132,6 +135,16 @@ __device__ __forceinline__ void gemm_store_chunk_bf16(bf16* out, long long ldo, 
 __device__ __forceinline__ void gemm_residual_prefetch(const GemmKParams& p, int row, int col0, uint4 (&rsd)[4]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) rsd[g] = make_uint4(0u, 0u, 0u, 0u);
+  if (p.transpose_out) {                                          // residual[c][row]: 32 two-byte loads; a warp reads 64 contiguous bytes per column
+    if (p.residual != nullptr && row < p.M) {
+      unsigned short* h = reinterpret_cast<unsigned short*>(rsd);
+      const unsigned short* src = reinterpret_cast<const unsigned short*>(p.residual) + row;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (col0 + e < p.N) h[e] = src[static_cast<long long>(col0 + e) * p.ldr];
+    }
+    return;
+  }
   if (p.residual != nullptr && row < p.M) {
     const bf16* src = p.residual + static_cast<long long>(row) * p.ldr + col0;
 #pragma unroll
@@ -185,6 +198,15 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         if (col0 + 4 * g < p.N) *reinterpret_cast<float4*>(o + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    return;
+  }
+  if (p.transpose_out) {                                          // out[c][row]: the lanes of a warp are 32 consecutive addresses (64 B = two whole sectors)
+    if (row < p.M) {
+      bf16* o = reinterpret_cast<bf16*>(p.out) + row;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (col0 + e < p.N) o[static_cast<long long>(col0 + e) * p.ldo] = __float2bfloat16_rn(v[e]);
     }
     return;
   }

@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("block_n", _i32),
         ("split_k", _i32),
         ("workspace", _vp), ("workspace_bytes", _i64),
-        ("tail_split", _i32), ("reserved", _i32),
+        ("tail_split", _i32), ("transpose_out", _i32),
         ("aux", _vp), ("ld_aux", _i64),
     ]
 

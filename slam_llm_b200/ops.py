@@ -72,7 +72,7 @@ def _gemm_workspace(device: torch.device) -> torch.Tensor:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1, tail_split: int = 0,
-         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+         aux: Optional[torch.Tensor] = None, transpose_out: bool = False) -> torch.Tensor:
     """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16.
     tail_split: 0 = automatic, -1 = off, n > 1 = at most n k-slices per tail tile.
     act 3 / 4 = fused SwiGLU forward / backward on the blocked-64 gate/up layout (see slam_gemm_args.aux): act 3 returns gu and
@@ -81,6 +81,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     M, K1 = a.shape
     N = b.shape[0]
     assert b.shape[1] == K1, (a.shape, b.shape)
+    if transpose_out:
+        return _gemm_swapped(a, b, out, a2, b2, residual, block_n)
     if split_k > 1:
         assert out_f32 and bias is None and residual is None and act == 0, "split_k needs a plain f32 output"
         if out is None:
@@ -124,6 +126,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     else:
         g.aux, g.ld_aux = None, 0
     g.block_n = block_n
+    g.transpose_out = 0
     g.split_k = split_k
     if tail_split == 0:
         tail_split = _TAIL_SPLIT_DEFAULT
@@ -139,6 +142,50 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
         _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
         e1.record()
         _GEMM_LOG.append((2.0 * M * N * (K1 + g.k2), e0, e1))
+        return out
+    _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
+    return out
+
+
+def _gemm_swapped(w, x, out, w2, x2, residual, block_n):
+    """transpose_out (swap-AB): returns y[Mx, Nw] = x @ w.T (+ x2 @ w2.T) (+ residual[Mx, Nw]) computed as tiles of (w @ x.T): the weight `w` [Nw, K]
+    is the M operand (its rows fill 256-row CTA-pair tiles exactly), the activations `x` [Mx, K] the N operand."""
+    Nw, K1 = w.shape
+    Mx = x.shape[0]
+    if out is None:
+        out = torch.empty((Mx, Nw), device=w.device, dtype=BF16)
+    _req(out, BF16, "gemm.out")
+    assert tuple(out.shape) == (Mx, Nw) and out.stride(1) == 1
+    g = _l.GemmArgs()
+    g.a, g.lda = w.data_ptr(), _row_major_2d(w, "gemm.a")
+    g.b, g.ldb = x.data_ptr(), _row_major_2d(x, "gemm.b")
+    g.k1 = K1
+    if w2 is not None:
+        _req(w2, BF16, "gemm.a2"); _req(x2, BF16, "gemm.b2")
+        assert w2.shape[0] == Nw and x2.shape[0] == Mx and w2.shape[1] == x2.shape[1]
+        g.k2 = w2.shape[1]
+        g.a2, g.lda2 = w2.data_ptr(), _row_major_2d(w2, "gemm.a2")
+        g.b2, g.ldb2 = x2.data_ptr(), _row_major_2d(x2, "gemm.b2")
+    else:
+        g.k2 = 0
+    g.out, g.ldo = out.data_ptr(), _row_major_2d(out, "gemm.out")
+    g.out_f32, g.act, g.bias, g.alpha = 0, 0, None, 1.0
+    if residual is not None:
+        _req(residual, BF16, "gemm.residual")
+        assert tuple(residual.shape) == (Mx, Nw)
+        g.residual, g.ldr = residual.data_ptr(), _row_major_2d(residual, "gemm.residual")
+    else:
+        g.residual, g.ldr = None, 0
+    g.m, g.n = Nw, Mx
+    g.aux, g.ld_aux = None, 0
+    g.block_n, g.split_k, g.tail_split, g.transpose_out = block_n, 1, -1, 1
+    g.workspace, g.workspace_bytes = None, 0
+    if _GEMM_LOG is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
+        e1.record()
+        _GEMM_LOG.append((2.0 * Mx * Nw * (K1 + g.k2), e0, e1))
         return out
     _l.check(_l.load().slam_gemm_bf16(C.byref(g), _stream()), "slam_gemm_bf16")
     return out

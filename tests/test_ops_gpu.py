@@ -410,6 +410,33 @@ def test_rmsnorm(ops, d):
     assert rel_err(dx, xr.grad + dres.float()) < 8e-3
 
 
+@pytest.mark.parametrize("tile", [0, 2000192, 2000224, 2000256, 128192, 128128])
+def test_gemm_transpose_out_swap_ab(ops, tile):
+    """transpose_out: the WEIGHT is the M operand (CTA-pair tiles without row padding), tokens are the N operand; the result still lands as
+    y[tokens, features] = x W^T + x2 W2^T + residual.  Integer-valued inputs: exact in fp32 accumulation -> bit-exact after bf16 rounding."""
+    Mx, Nw, K, r = 1604, 768, 320, 64
+    g = torch.Generator(device="cuda").manual_seed(91)
+    x = torch.randint(-3, 4, (Mx, K), generator=g, device="cuda").to(BF16)
+    w = torch.randint(-3, 4, (Nw, K), generator=g, device="cuda").to(BF16)
+    x2 = torch.randint(-2, 3, (Mx, r), generator=g, device="cuda").to(BF16)
+    w2 = torch.randint(-2, 3, (Nw, r), generator=g, device="cuda").to(BF16)
+    res = torch.randint(-8, 9, (Mx, Nw), generator=g, device="cuda").to(BF16)
+    want = x.float() @ w.float().t()
+    y = ops.gemm(w, x, transpose_out=True, block_n=tile)
+    assert y.shape == (Mx, Nw) and torch.equal(y.float(), want.to(BF16).float())
+    want2 = want + x2.float() @ w2.float().t() + res.float()
+    y2 = ops.gemm(w, x, a2=w2, b2=x2, residual=res, transpose_out=True, block_n=tile)
+    assert torch.equal(y2.float(), want2.to(BF16).float())
+    # in-place residual (out aliases residual), as the decoder's o / down projections use it
+    buf = res.clone()
+    ops.gemm(w, x, residual=buf, out=buf, transpose_out=True, block_n=tile)
+    assert torch.equal(buf.float(), (want + res.float()).to(BF16).float())
+    # strided output rows (a column slice of a wider buffer)
+    wide = torch.zeros(Mx, Nw + 64, device="cuda", dtype=BF16)
+    ops.gemm(w, x, out=wide[:, 32: 32 + Nw], transpose_out=True, block_n=tile)
+    assert torch.equal(wide[:, 32: 32 + Nw].float(), want.to(BF16).float()) and float(wide[:, :32].abs().max()) == 0.0
+
+
 def _rope_tables(S, dh, theta):
     inv = 1.0 / (theta ** (torch.arange(0, dh, 2, dtype=F32, device=dev()) / dh))
     fr = torch.outer(torch.arange(S, dtype=F32, device=dev()), inv)
