@@ -585,7 +585,7 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   using namespace slam;
   SLAM_CHECK_ARG(g != nullptr, "gemm: null args");
   SLAM_CHECK_ARG(g->m > 0 && g->n > 0 && g->k1 > 0, "gemm: bad shape m=%d n=%d k1=%d", g->m, g->n, g->k1);
-  SLAM_CHECK_ARG(g->n % 8 == 0, "gemm: n=%d must be a multiple of 8", g->n);
+  SLAM_CHECK_ARG(g->n % 8 == 0 || g->transpose_out != 0, "gemm: n=%d must be a multiple of 8", g->n);   // (transposed stores are per element)
   SLAM_CHECK_ARG(g->transpose_out != 0 || (g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0),
                  "gemm: output must be 16-byte aligned with ldo %% 8 == 0");
   SLAM_CHECK_ARG(g->residual == nullptr || g->transpose_out != 0 || (g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0),
