@@ -81,6 +81,20 @@ def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch
     return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out=_THIN_POOL.take(M, N, a.device), out_f32=True, split_k=split))
 
 
+_SWAP_AB = os.environ.get("SLAM_SWAP_AB", "1") != "0"
+
+
+def _swap_ab(tokens: int, features: int) -> bool:
+    """Swap-AB for the decoder linears (slam_gemm_args.transpose_out): the weight becomes the 256-row M operand of CTA-pair tiles and the token
+    dimension the 192-wide N.  Pays when the token count does not fill 256-row pair tiles (M = 1604: 7 pair tiles = 10.5 % padding the other way
+    round) while the feature count does.  Measured at M = 1604 (tools/swap_probe.py, steady state): +1.4 ... +4.0 % over the best non-swapped tile on
+    qkv / o / down / d_gate_up / d_qkv."""
+    if not _SWAP_AB or features % 256 != 0 or tokens < 512:
+        return False
+    pad = (-tokens) % 256
+    return pad * 25 > tokens                      # more than 4 % of a pair grid would be padding rows
+
+
 def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
@@ -595,7 +609,10 @@ class LlamaLoRAB200:
     def _lin_fwd(self, x, w, gname: str, li: int, residual=None, out=None, bias=None):
         """y = x W^T (+ bias) (+ residual) + (dropout(x) A_cat^T)(s B_cat)^T  ->  (y, saved) with saved = (x_lora, T, seed) for the backward."""
         info = self.groups.get(gname)
+        swap = bias is None and _swap_ab(x.shape[0], w.shape[0])
         if info is None:
+            if swap:
+                return ops.gemm(w, x, residual=residual, out=out, transpose_out=True), None
             return ops.gemm(x, w, residual=residual, out=out, bias=bias), None
         p, seed = self.dropout_p if self.dropout_active else 0.0, 0
         x_lora = x
@@ -603,18 +620,24 @@ class LlamaLoRAB200:
             seed = self._drop_seed(li, gname)
             x_lora = ops.dropout(x, p, seed)                                             # lora_A(dropout(x)): LoRA branch only
         t = _gemm_few_tiles(x_lora, info["a_cat"][li])                                   # T = x A_cat^T  [M, rpad]
-        y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias)   # fused base + LoRA tile
+        if swap:                                                                         # y^T tiles = W x^T + (s B_cat) T^T: same fused tile, operands swapped
+            y = ops.gemm(w, x, a2=info["b_cat"][li], b2=t, residual=residual, out=out, transpose_out=True)
+        else:
+            y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias)   # fused base + LoRA tile
         return y, (x_lora, t, p, seed)
 
     def _lin_bwd(self, dy, wT, gname: str, li: int, saved):
         """dX = dY W + mask o ((dY sB) A)  and LoRA grads (dA = U^T x_lora, dB^T = s T^T dY) into the arena."""
         info = self.groups.get(gname)
+        swap = _swap_ab(dy.shape[0], wT.shape[0])
         if info is None:
-            return ops.gemm(dy, wT)
+            return ops.gemm(wT, dy, transpose_out=True) if swap else ops.gemm(dy, wT)
         x_lora, t, p, seed = saved
         u = _gemm_few_tiles(dy, info["b_catT"][li])                                      # U = dY (s B)  [M, rpad]
         if p > 0.0:
             dx = ops.dropout_bwd_add(ops.gemm(dy, wT), ops.gemm(u, info["a_catT"][li]), p, seed)
+        elif swap:
+            dx = ops.gemm(wT, dy, a2=info["a_catT"][li], b2=u, transpose_out=True)
         else:
             dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li])                           # fused: one accumulator tile
         r, s = self.lora.r, self.lora.scaling
