@@ -99,8 +99,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int tile = item / p.ksplit;
       const int kb_begin = (item % p.ksplit) * p.kb_per_split;
       const int kb_end = min(nkb, kb_begin + p.kb_per_split);
-      const int row_a = (tile % p.num_m_tiles) * 256 + static_cast<int>(rank) * 128;
-      const int row_b = (tile / p.num_m_tiles) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+      // tile order: M fastest (consecutive pairs share a B tile = weight tile of the normal orientation).  Swap-AB (transpose_out): the weight
+      // is the A operand, so N runs fastest and the pairs that work at the same time share the big operand again.
+      const int m_tile = p.transpose_out ? tile / p.num_n_tiles : tile % p.num_m_tiles;
+      const int n_tile = p.transpose_out ? tile % p.num_n_tiles : tile / p.num_m_tiles;
+      const int row_a = m_tile * 256 + static_cast<int>(rank) * 128;
+      const int row_b = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], ph ^ 1u);
         if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
@@ -161,8 +165,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t it = 0;
     for (int item = pair; item < total_items; item += npairs, ++it) {
       const int tile = item / p.ksplit;
-      const int m_tile = tile % p.num_m_tiles;
-      const int n_tile = tile / p.num_m_tiles;
+      const int m_tile = p.transpose_out ? tile / p.num_n_tiles : tile % p.num_m_tiles;
+      const int n_tile = p.transpose_out ? tile % p.num_n_tiles : tile / p.num_m_tiles;
       const uint32_t acc = it % ACC_STAGES;
       const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tfull_bar[acc], aph);
