@@ -41,7 +41,8 @@ def _digest(src: Path, flags) -> str:
 
 def build(force: bool = False, watchdog: bool = True, verbose: bool = True) -> Path:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = list(NVCC_FLAGS) + [f"-DSLAM_WATCHDOG={1 if watchdog else 0}"]
+    flags = list(NVCC_FLAGS) + [f"-DSLAM_WATCHDOG={1 if watchdog else 0}"] + os.environ.get("SLAM_NVCC_EXTRA", "").split()
+    lib = Path(os.environ["SLAM_B200_LIB_OUT"]) if os.environ.get("SLAM_B200_LIB_OUT") else LIB     # experiment builds: another output file
     OBJ.mkdir(exist_ok=True)
     objs, jobs = [], []
     for src in _sources():
@@ -66,14 +67,14 @@ def build(force: bool = False, watchdog: bool = True, verbose: bool = True) -> P
             for name in ex.map(compile_one, jobs):
                 if verbose:
                     print(f"[slam_b200.build] compiled {name}", file=sys.stderr)
-    if jobs or not LIB.exists():
-        cmd = [nvcc, "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if jobs or not lib.exists():
+        cmd = [nvcc, "-shared", "-o", str(lib)] + [str(o) for o in objs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
-            print(f"[slam_b200.build] linked {LIB}", file=sys.stderr)
-    return LIB
+            print(f"[slam_b200.build] linked {lib}", file=sys.stderr)
+    return lib
 
 
 if __name__ == "__main__":

@@ -43,8 +43,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// SLAM_WAIT_HINT_NS > 0: pass a suspend-time hint to try_wait (the waiting warp may be parked that long before the instruction returns false):
+// fewer wake-ups of the 8 epilogue warps + producer while a long MMA main loop runs (experiment knob; 0 = hardware default).
+#ifndef SLAM_WAIT_HINT_NS
+#define SLAM_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SLAM_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(SLAM_WAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -52,6 +66,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
