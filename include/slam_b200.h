@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SLAM_B200_ABI_VERSION 5
+#define SLAM_B200_ABI_VERSION 6
 
 int slam_abi_version(void);
 const char* slam_last_error(void);
@@ -56,7 +56,9 @@ typedef struct slam_gemm_args {
   int32_t m, n;
   int32_t block_n;                /* tile override: 0 = auto; 64/128/192/256 = BLOCK_N with 128-row tiles;
                                      BLOCK_M*1000+BLOCK_N (e.g. 256256) = explicit 256-row tile;
-                                     2000000+BLOCK_N (256/224/192/160/128) = CTA-pair kernel (cta_group::2: 256 x BLOCK_N per SM pair) */
+                                     2000000+BLOCK_N (256/224/192/160/128) = CTA-pair kernel (cta_group::2: 256 x BLOCK_N per SM pair);
+                                     3000064 = thin-product kernel (N <= 64: a cluster of 8 CTAs per 128-row tile splits K and reduces the
+                                     partial tiles through distributed shared memory in a fixed order; what auto picks for such products) */
   int32_t split_k;                /* <= 1: off.  > 1: K is cut into that many slices processed by different CTAs and merged with
                                      fp32 atomics into `out`, which must be f32 and ZERO-INITIALISED by the caller; no bias /
                                      activation / residual (thin LoRA products, lm_head dgrad: few output tiles, long K) */
@@ -81,6 +83,13 @@ typedef struct slam_gemm_args {
                                      act 4: the product is dh [M, N = F] (never stored); aux (bf16 [M, 2F], read) = gu, and
                                             out (bf16 [M, 2F]) = d(gu) - identical to slam_swiglu_bwd(gu, bf16(dh)).
                                      Both need bf16 out, no bias / residual / split_k; act 3 needs tiles of 128 or 256 columns */
+  int32_t static_operands;        /* bit 0: A, bit 1: B is CONSTANT for the lifetime of the stream's in-flight work (frozen weights - the
+                                     reference's frozen encoder / LLM, models/slam_model.py:104-160): not written by any kernel that can still be
+                                     running when this one starts.  The CTA-pair kernels then request the first ring of that operand's tiles
+                                     BEFORE griddepcontrol.wait, i.e. under the tail of the preceding kernel (programmatic dependent launch), so
+                                     the HBM latency of the first weight tiles is not paid after it (tools/gemm_trace.py: 2.6-3.3 us per launch).
+                                     0 = nothing is assumed */
+  int32_t reserved0;
 } slam_gemm_args;
 int slam_gemm_bf16(const slam_gemm_args* args, void* stream);
 /* bytes of `workspace` the tail split needs on the current device (SM count x one 128 x 256 fp32 tile + flags) */

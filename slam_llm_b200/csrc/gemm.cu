@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "gemm_2cta.cuh"
+#include "gemm_thin.cuh"
 #include "host.cuh"
 
 namespace slam {
@@ -234,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = slice; j < NL; j += S) {
             const int c = h + 2 * j;
             uint4 rsd[4];
-            gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
+            gemm_residual_prefetch(p, row_base, lane, n0 + c * 32, rsd);
             uint32_t r[32];
             tmem_ld_32x32(taddr + c * 32, r);
             tmem_ld_wait();
@@ -299,7 +300,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = h; c < NCH; c += 2) {
           uint4 rsd[4], rsd2[4];
           if (p.act == 4) gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
-          else gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
+          else gemm_residual_prefetch(p, row_base, lane, n0 + c * 32, rsd);
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -383,6 +384,7 @@ static void fill_kparams(const slam_gemm_args* g, int block_m, int block_n, Gemm
   p.ld_aux = g->ld_aux;
   p.alpha = g->alpha;
   p.transpose_out = g->transpose_out != 0 ? 1 : 0;
+  p.static_ops = g->static_operands & 3;
   p.ksplit = g->split_k > 1 ? g->split_k : 1;
   const int nkb_total = p.kb1 + p.kb2;
   if (p.ksplit > nkb_total) p.ksplit = nkb_total;
@@ -482,6 +484,10 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
   return 0;
 }
 
+#ifdef SLAM_GEMM_TRACE
+static int g_trace_host_launch = 0;
+#endif
+
 template <int BLOCK_N>
 static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
   using Cfg = GemmPairCfg<BLOCK_N>;
@@ -507,6 +513,9 @@ static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
   }
   GemmKParams p;
   fill_kparams(g, 256, BLOCK_N, p);
+#ifdef SLAM_GEMM_TRACE
+  p.trace_id = g_trace_host_launch++;
+#endif
   const int items = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int max_pairs = num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
@@ -526,6 +535,54 @@ static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
     return static_cast<int>(le);
   }
   SLAM_LAUNCH_CHECK("slam_gemm_bf16.pair");
+  return 0;
+}
+
+// Thin product (N <= 64, one K segment, plain bf16 output): a cluster of THIN_SPLIT CTAs per 128-row tile (gemm_thin.cuh)
+static bool thin_cluster_applies(const slam_gemm_args* g) {
+  const int64_t nkb = ceil_div(g->k1, GEMM_BK);
+  return g->n <= THIN_BN && g->k2 == 0 && !g->out_f32 && g->act == 0 && g->bias == nullptr && g->residual == nullptr && g->split_k <= 1 &&
+         g->transpose_out == 0 && nkb >= 2 * THIN_SPLIT && ceil_div(g->m, 128) * THIN_SPLIT <= 2 * num_sms();
+}
+
+static int launch_gemm_thin(const slam_gemm_args* g, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_thin_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm(thin): cudaFuncSetAttribute(smem=%d) failed: %s", THIN_SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap(&tmA, g->a, g->m, g->k1, g->lda, 128)) != 0) return rc;
+  if ((rc = make_tmap(&tmB, g->b, g->n, g->k1, g->ldb, THIN_BN)) != 0) return rc;
+  ThinParams p;
+  p.M = g->m;
+  p.N = g->n;
+  p.nkb = static_cast<int>(ceil_div(g->k1, GEMM_BK));
+  p.kb_per_cta = static_cast<int>(ceil_div(p.nkb, THIN_SPLIT));
+  p.out = reinterpret_cast<bf16*>(g->out);
+  p.ldo = g->ldo;
+  p.alpha = g->alpha;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(THIN_SPLIT * ceil_div(g->m, 128)));   // cluster dims (THIN_SPLIT,1,1) are compiled into the kernel
+  cfg.blockDim = dim3(THIN_THREADS);
+  cfg.dynamicSmemBytes = THIN_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_thin_cluster_kernel, tmA, tmB, p);
+  if (le != cudaSuccess) {
+    set_error("slam_gemm_bf16(thin): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return static_cast<int>(le);
+  }
+  SLAM_LAUNCH_CHECK("slam_gemm_bf16.thin");
   return 0;
 }
 
@@ -581,14 +638,27 @@ static int pick_tile(int m, int n, int k, bool tail_split, bool allow_pair, bool
 
 extern "C" int64_t slam_gemm_workspace_bytes(void) { return slam::sk_workspace_bytes(); }
 
+#ifdef SLAM_GEMM_TRACE
+// debug build: buf = device memory of launches x TRACE_CTAS x TRACE_EV x 2 u64 (zeroed by the caller), or NULL to stop; returns the pair launches since the previous call
+extern "C" int slam_debug_gemm_trace(void* buf, int launches) {
+  const int n = slam::g_trace_host_launch;
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  cudaMemcpyToSymbol(slam::g_trace_buf, &b, sizeof(b));
+  cudaMemcpyToSymbol(slam::g_trace_launches, &launches, sizeof(launches));
+  slam::g_trace_host_launch = 0;
+  return n;
+}
+#endif
+
 extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
   using namespace slam;
   SLAM_CHECK_ARG(g != nullptr, "gemm: null args");
   SLAM_CHECK_ARG(g->m > 0 && g->n > 0 && g->k1 > 0, "gemm: bad shape m=%d n=%d k1=%d", g->m, g->n, g->k1);
-  SLAM_CHECK_ARG(g->n % 8 == 0 || g->transpose_out != 0, "gemm: n=%d must be a multiple of 8", g->n);   // (transposed stores are per element)
-  SLAM_CHECK_ARG(g->transpose_out != 0 || (g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0),
-                 "gemm: output must be 16-byte aligned with ldo %% 8 == 0");
-  SLAM_CHECK_ARG(g->residual == nullptr || g->transpose_out != 0 || (g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0),
+  // 16-byte pieces run along n (normal orientation) or along m (transpose_out: out / residual are [n][m])
+  SLAM_CHECK_ARG((g->transpose_out != 0 ? g->m : g->n) % 8 == 0, "gemm: %s=%d must be a multiple of 8", g->transpose_out != 0 ? "m" : "n",
+                 g->transpose_out != 0 ? g->m : g->n);
+  SLAM_CHECK_ARG(g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0, "gemm: output must be 16-byte aligned with ldo %% 8 == 0");
+  SLAM_CHECK_ARG(g->residual == nullptr || (g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0),
                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
   SLAM_CHECK_ARG(g->bias == nullptr || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   SLAM_CHECK_ARG(g->k2 == 0 || (g->a2 != nullptr && g->b2 != nullptr), "gemm: k2 > 0 needs a2/b2");
@@ -605,6 +675,12 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
                  "gemm: transpose_out needs a bf16 output and no bias / activation / split_k");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
+  if (tile == 3000064) {   // thin cluster kernel, explicitly
+    SLAM_CHECK_ARG(thin_cluster_applies(g), "gemm: tile 3000064 (thin cluster kernel) needs n <= 64, one K segment of >= %d k-blocks, a plain bf16 output",
+                   2 * THIN_SPLIT);
+    return launch_gemm_thin(g, st);
+  }
+  if (tile == 0 && thin_cluster_applies(g)) return launch_gemm_thin(g, st);
   if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1 && g->act < 3, g->split_k <= 1, g->act == 3, g->act == 4);
   SLAM_CHECK_ARG(g->act != 3 || (tile % 1000) % 128 == 0, "gemm: SwiGLU forward needs a tile of 128 or 256 columns (tile %d)", tile);
   if (tile < 1000) tile += 128 * 1000;   // (2000000 + BLOCK_N = CTA-pair kernel)

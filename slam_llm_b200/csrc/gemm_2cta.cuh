@@ -56,6 +56,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t rank = cluster_ctarank();
   const int pair = static_cast<int>(blockIdx.x >> 1);
   const int npairs = static_cast<int>(gridDim.x >> 1);
+  if (threadIdx.x == 0) SLAM_TRACE(0);                      // kernel entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -84,8 +85,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   cluster_sync_all();      // barriers of BOTH CTAs are initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SLAM_TRACE(1);                      // prologue done (barriers, TMEM, cluster sync)
   pdl_trigger();
-  pdl_wait();
 
   const int total_items = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // num_m_tiles counts 256-row pair tiles
   const int nkb = p.kb1 + p.kb2;
@@ -94,28 +95,59 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ------------------------------------------------------------ TMA producer (both CTAs; whole warp, elected lane issues)
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
     const uint32_t full_leader = mapa_shared(smem_u32(full_bar), 0);
-    uint32_t stage = 0, ph = 0;
-    for (int item = pair; item < total_items; item += npairs) {
+    // tile order: M fastest (consecutive pairs share a B tile = weight tile of the normal orientation).  Swap-AB (transpose_out): the weight
+    // is the A operand, so N runs fastest and the pairs that work at the same time share the big operand again.
+    auto rows_of = [&](int item, int& row_a, int& row_b) {
       const int tile = item / p.ksplit;
-      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
-      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
-      // tile order: M fastest (consecutive pairs share a B tile = weight tile of the normal orientation).  Swap-AB (transpose_out): the weight
-      // is the A operand, so N runs fastest and the pairs that work at the same time share the big operand again.
       const int m_tile = p.transpose_out ? tile / p.num_n_tiles : tile % p.num_m_tiles;
       const int n_tile = p.transpose_out ? tile % p.num_n_tiles : tile / p.num_m_tiles;
-      const int row_a = m_tile * 256 + static_cast<int>(rank) * 128;
-      const int row_b = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+      row_a = m_tile * 256 + static_cast<int>(rank) * 128;
+      row_b = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+    };
+    // Frozen operands (static_ops) do not depend on the preceding kernel: the first ring of their tiles is requested BEFORE
+    // griddepcontrol.wait, under that kernel's tail.  Each such stage is armed for its full byte count; the dependent operand of the
+    // same stages follows after the wait (`pre` k-blocks of the first work item, all inside the first K segment).
+    int pre = 0;
+    if (p.static_ops != 0 && pair < total_items) {
+      int row_a, row_b;
+      rows_of(pair, row_a, row_b);
+      const int kb_begin = (pair % p.ksplit) * p.kb_per_split;
+      const int kb_end = min(min(nkb, kb_begin + p.kb_per_split), p.kb1);
+      pre = max(0, min(STAGES, kb_end - kb_begin));
+      for (int s = 0; s < pre; ++s) {
+        if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&full_bar[s]), 2 * Cfg::STAGE_BYTES);
+        const uint32_t fb = full_leader + s * 8;
+        if (p.static_ops & 1) tma_load_2d_pair_elect(sA_u + s * Cfg::A_BYTES, &tmA, fb, (kb_begin + s) * GEMM_BK, row_a);
+        if (p.static_ops & 2) tma_load_2d_pair_elect(sB_u + s * Cfg::B_BYTES, &tmB, fb, (kb_begin + s) * GEMM_BK, row_b);
+      }
+    }
+    pdl_wait();                                             // everything else may have been written by the preceding kernel
+    if (lane == 0) SLAM_TRACE(2);
+    uint32_t stage = 0, ph = 0;
+    for (int item = pair; item < total_items; item += npairs) {
+      const int kb_begin = (item % p.ksplit) * p.kb_per_split;
+      const int kb_end = min(nkb, kb_begin + p.kb_per_split);
+      int row_a, row_b;
+      rows_of(item, row_a, row_b);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[stage], ph ^ 1u);
-        if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
         const uint32_t fb = full_leader + stage * 8;
-        if (kb < p.kb1) {
-          tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA, fb, kb * GEMM_BK, row_a);
-          tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB, fb, kb * GEMM_BK, row_b);
+        if (pre > 0) {                                      // stage armed above, frozen operand in flight: only the dependent one is missing
+          --pre;
+          if (!(p.static_ops & 1)) tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA, fb, kb * GEMM_BK, row_a);
+          if (!(p.static_ops & 2)) tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB, fb, kb * GEMM_BK, row_b);
+          if (lane == 0 && kb == kb_begin) SLAM_TRACE(3);
         } else {
-          const int k2 = kb - p.kb1;
-          tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA2, fb, k2 * GEMM_BK, row_a);
-          tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB2, fb, k2 * GEMM_BK, row_b);
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          if (lane == 0 && item == pair && kb == kb_begin) SLAM_TRACE(3);   // first TMA load issued
+          if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+          if (kb < p.kb1) {
+            tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA, fb, kb * GEMM_BK, row_a);
+            tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB, fb, kb * GEMM_BK, row_b);
+          } else {
+            const int k2 = kb - p.kb1;
+            tma_load_2d_pair_elect(sA_u + stage * Cfg::A_BYTES, &tmA2, fb, k2 * GEMM_BK, row_a);
+            tma_load_2d_pair_elect(sB_u + stage * Cfg::B_BYTES, &tmB2, fb, k2 * GEMM_BK, row_b);
+          }
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -125,6 +157,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only; whole warp, uniform operands)
+    // (touches shared / tensor memory only, behind the full barriers: no griddepcontrol.wait of its own)
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
       const uint32_t my_a = sw128_kmajor_desc_lo(smem_u32(sA) + (lane < STAGES ? lane : 0) * Cfg::A_BYTES);
@@ -143,11 +176,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], ph);
           tc_fence_after();
+          if (lane == 0 && it == 0 && kb == kb_begin) SLAM_TRACE(4);      // first operands have landed
+          if (lane == 0 && it == 0 && kb == kb_begin + 8) SLAM_TRACE(14); // ... and the 9th k-block (ring refilled once)
           const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, stage);
           const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, stage);
           umma_kblock_pair(d_tmem, a_lo, b_lo, idesc, kb > kb_begin ? 1u : 0u);
           umma_commit_pair_elect(empty_u + stage * 8);
           if (kb == kb_end - 1) umma_commit_pair_elect(tfull_u + acc * 8);
+          if (lane == 0 && kb == kb_end - 1) SLAM_TRACE(it == 0 ? 5 : 6);  // last MMA of the first / of the latest tile issued
           if (++stage == STAGES) {
             stage = 0;
             ph ^= 1u;
@@ -157,6 +193,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (both CTAs, each drains its own 128 rows; 8 warps)
+    pdl_wait();                                             // residual / aux reads and the output writes depend on the preceding kernel
     const int e = warp - 4;
     const int q = e & 3, h = e >> 2;
     uint8_t* stg = epi_stage + e * (32 * GEMM_EPI_PITCH);
@@ -171,6 +208,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t aph = (it / ACC_STAGES) & 1u;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
+      if (e == 0 && lane == 0) SLAM_TRACE(it == 0 ? 7 : 9);             // accumulator of the first / latest tile complete
       const int n0 = n_tile * BLOCK_N;
       const int row_base = m_tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
@@ -204,7 +242,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int c = h; c < NCH; c += 2) {
         uint4 rsd[4], rsd2[4];
         if (p.act == 4) gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
-        else gemm_residual_prefetch(p, row_base + lane, n0 + c * 32, rsd);
+        else gemm_residual_prefetch(p, row_base, lane, n0 + c * 32, rsd);
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -215,13 +253,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (p.act == 4) gemm_epilogue_swiglu_bwd(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
         else gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
       }
+      if (e == 0 && lane == 0) {
+        SLAM_TRACE(it == 0 ? 8 : 10);                                     // epilogue of the first / latest tile done (warp 4's share)
+        SLAM_TRACE_V(13, it + 1);                                         // tiles done by this CTA
+      }
     }
   }
+  if (threadIdx.x == 0) SLAM_TRACE(11);                     // this thread's role finished
 
   tc_fence_before();
   cluster_sync_all();      // no CTA of the pair may exit (or free TMEM) while the other can still touch its memory
   tc_fence_after();
   if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) SLAM_TRACE(12);                     // exit
 }
 
 }  // namespace slam

@@ -32,7 +32,32 @@ struct GemmKParams {
   int transpose_out;          // 1: the tile is C^T of the logical output: element (row r, col c) of the accumulator goes to out[c * ldo + r] (bf16),
                               //    the residual is read the same way.  Lets the WEIGHT be the 256-row M operand of a CTA pair (rows % 256 == 0,
                               //    no tile padding) while the token dimension becomes the flexible-width N (swap-AB, what cuBLAS does for M = 1604).
+  int static_ops;             // slam_gemm_args.static_operands: bit 0 / 1 = the A / B operand may be loaded before griddepcontrol.wait
+#ifdef SLAM_GEMM_TRACE
+  int trace_id;               // debug build: launch number (host counter)
+#endif
 };
+
+// Debug build only (SLAM_NVCC_EXTRA=-DSLAM_GEMM_TRACE, tools/gemm_trace.py): time stamps from inside the CTA-pair kernel.
+// g_trace_buf[launch % g_trace_launches][cta < TRACE_CTAS][event] = {globaltimer ns, clock64}.
+#ifdef SLAM_GEMM_TRACE
+constexpr int TRACE_EV = 16, TRACE_CTAS = 160;
+static __device__ unsigned long long* g_trace_buf = nullptr;
+static __device__ int g_trace_launches = 0;
+__device__ __forceinline__ void trace_ev(int launch, int ev, unsigned long long value = ~0ull) {
+  if (g_trace_buf == nullptr || blockIdx.x >= TRACE_CTAS) return;
+  unsigned long long gt;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+  unsigned long long* slot = g_trace_buf + ((static_cast<size_t>(launch % g_trace_launches) * TRACE_CTAS + blockIdx.x) * TRACE_EV + ev) * 2;
+  slot[0] = value != ~0ull ? value : gt;
+  slot[1] = static_cast<unsigned long long>(clock64());
+}
+#define SLAM_TRACE(ev) trace_ev(p.trace_id, ev)
+#define SLAM_TRACE_V(ev, v) trace_ev(p.trace_id, ev, static_cast<unsigned long long>(v))
+#else
+#define SLAM_TRACE(ev) ((void)0)
+#define SLAM_TRACE_V(ev, v) ((void)0)
+#endif
 
 // One unit of work of a persistent CTA: k-blocks [kb_begin, kb_end) of one output tile.
 //   kind 0  the accumulation is final for this CTA's purposes (whole tile, or a split-K slice merged with atomics);
@@ -132,20 +157,25 @@ __device__ __forceinline__ void gemm_store_chunk_bf16(bf16* out, long long ldo, 
   __syncwarp();
 }
 
-__device__ __forceinline__ void gemm_residual_prefetch(const GemmKParams& p, int row, int col0, uint4 (&rsd)[4]) {
+// Residual of one 32 x 32 chunk, requested BEFORE the TMEM load.  Normal orientation: rsd = this thread's row, 32 columns.  Swap-AB
+// (transpose_out): the residual is [column][row] in memory, so the warp fetches it in the memory layout - rsd[i] = 8 consecutive rows
+// (row_base + 8 (lane % 4) ...) of column col0 + 8 i + lane / 4, one 16-byte load each - and gemm_epilogue_chunk transposes it through
+// the staging tile.  (Round 2 measured the first version, 32 two-byte loads per thread, at +22 us per 256 x 192 tile: tools/gemm_trace.py.)
+__device__ __forceinline__ void gemm_residual_prefetch(const GemmKParams& p, int row_base, int lane, int col0, uint4 (&rsd)[4]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) rsd[g] = make_uint4(0u, 0u, 0u, 0u);
-  if (p.transpose_out) {                                          // residual[c][row]: 32 two-byte loads; a warp reads 64 contiguous bytes per column
-    if (p.residual != nullptr && row < p.M) {
-      unsigned short* h = reinterpret_cast<unsigned short*>(rsd);
-      const unsigned short* src = reinterpret_cast<const unsigned short*>(p.residual) + row;
+  if (p.residual == nullptr) return;
+  if (p.transpose_out) {
+    const int r0 = row_base + 8 * (lane & 3);
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (col0 + e < p.N) h[e] = src[static_cast<long long>(col0 + e) * p.ldr];
+    for (int i = 0; i < 4; ++i) {
+      const int c = col0 + 8 * i + (lane >> 2);
+      if (c < p.N && r0 < p.M) rsd[i] = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(c) * p.ldr + r0);
     }
     return;
   }
-  if (p.residual != nullptr && row < p.M) {
+  const int row = row_base + lane;
+  if (row < p.M) {
     const bf16* src = p.residual + static_cast<long long>(row) * p.ldr + col0;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -175,7 +205,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
   }
-  if (p.residual != nullptr) {
+  if (p.residual != nullptr && !p.transpose_out) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float2 r0 = unpack_bf16x2(rsd[g].x), r1 = unpack_bf16x2(rsd[g].y), r2 = unpack_bf16x2(rsd[g].z), r3 = unpack_bf16x2(rsd[g].w);
@@ -201,13 +231,32 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
     }
     return;
   }
-  if (p.transpose_out) {                                          // out[c][row]: the lanes of a warp are 32 consecutive addresses (64 B = two whole sectors)
-    if (row < p.M) {
-      bf16* o = reinterpret_cast<bf16*>(p.out) + row;
+  if (p.transpose_out) {
+    // out[column][row] (bf16).  The thread holds one accumulator row x 32 columns; memory wants 8 consecutive ROWS of one column per 16-byte
+    // piece.  Both directions go through the warp's staging tile laid out [column][32 rows] (64 B + pad per column): two-byte shared-memory
+    // accesses on the thread = row side (a warp touches 64 contiguous bytes: conflict-free), 16-byte accesses on the memory side.
+    const int piece = lane & 3, cl = lane >> 2;
+    if (p.residual != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece) = rsd[i];
+      __syncwarp();
 #pragma unroll
       for (int e = 0; e < 32; ++e)
-        if (col0 + e < p.N) o[static_cast<long long>(col0 + e) * p.ldo] = __float2bfloat16_rn(v[e]);
+        v[e] += __bfloat162float(*reinterpret_cast<const bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane));
+      __syncwarp();
     }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) *reinterpret_cast<bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane) = __float2bfloat16_rn(v[e]);
+    __syncwarp();
+    bf16* o = reinterpret_cast<bf16*>(p.out);
+    const int r0 = row_base + 8 * piece;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = col0 + 8 * i + cl;
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece);
+      if (c < p.N && r0 < p.M) *reinterpret_cast<uint4*>(o + static_cast<long long>(c) * p.ldo + r0) = val;
+    }
+    __syncwarp();
     return;
   }
   uint32_t pk[16];

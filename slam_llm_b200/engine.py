@@ -60,16 +60,17 @@ class _ZeroPool:
 
 
 _THIN_POOL = _ZeroPool()
+_THIN_CLUSTER = os.environ.get("SLAM_THIN_CLUSTER", "1") != "0"      # A/B switch for the thin-product cluster kernel
 
 
 def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch.Tensor:
     """bf16 out = a @ b.T (+ a2 @ b2.T) for products with few output tiles but a long K (LoRA rank-64 products, lm_head dgrad):
     wide outputs (N >= 256) use the GEMM's own tail split (k-slices on idle SMs, deterministic exchange, bf16 epilogue);
-    thin ones (rank-64 LoRA products: two 32-column chunks per tile) split K over otherwise idle SMs with fp32 atomics into a
-    zeroed buffer, then one cast back to bf16."""
+    thin ones (rank-64 LoRA products, N <= 64) go to the cluster kernel of the library (8 CTAs per tile split K and reduce through distributed
+    shared memory: csrc/gemm_thin.cuh); what is left (a second K segment) splits K with fp32 atomics into a zeroed buffer + one cast."""
     M, K = a.shape
     N = b.shape[0]
-    if N >= 256:
+    if N >= 256 or (N <= 64 and a2 is None and _THIN_CLUSTER):
         return ops.gemm(a, b, a2=a2, b2=b2)
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 64 else 1)
     nkb = (K + 63) // 64 + ((a2.shape[1] + 63) // 64 if a2 is not None else 0)
@@ -77,11 +78,12 @@ def _gemm_few_tiles(a: torch.Tensor, b: torch.Tensor, a2=None, b2=None) -> torch
     if nkb < 128:      # measured (tools/thin_probe.py, M=1604 N=64): K=4096 16.5 us unsplit vs 22.8 us split-8 + cast; K=6144 22.4 vs 23.8; K=14336 46.1 vs 26.9
         split = 1
     if split <= 1:
-        return ops.gemm(a, b, a2=a2, b2=b2)
+        return ops.gemm(a, b, a2=a2, b2=b2, block_n=64 if N <= 64 else 0)          # (explicit 128 x 64 tile: `auto` would pick the cluster kernel)
     return ops.cast_bf16(ops.gemm(a, b, a2=a2, b2=b2, out=_THIN_POOL.take(M, N, a.device), out_f32=True, split_k=split))
 
 
 _SWAP_AB = os.environ.get("SLAM_SWAP_AB", "1") != "0"
+_STATIC_W = os.environ.get("SLAM_STATIC_W", "1") != "0"     # frozen weights are declared to the GEMM (slam_gemm_args.static_operands); 0 = A/B switch
 
 
 def _swap_ab(tokens: int, features: int) -> bool:
@@ -204,26 +206,26 @@ class WhisperEncoderB200:
         d, H = cfg.d, cfg.heads
         dh = d // H
         col1 = ops.conv_im2col(mel.contiguous(), 1, self.k1)
-        x1 = ops.gemm(col1, self.conv1_w, bias=self.conv1_b, act=1)                       # GELU(conv1)
+        x1 = ops.gemm(col1, self.conv1_w, bias=self.conv1_b, act=1, static_w=_STATIC_W)                       # GELU(conv1)
         col2 = ops.conv_im2col(x1.view(B, T, d), 2, 3 * d)
         Tp = (T + 1) // 2
         if Tp > self.pos.shape[0]:
             raise ValueError(f"audio too long for positional_embedding: {Tp} > {self.pos.shape[0]}")
-        x = ops.gemm(col2, self.conv2_w, bias=self.conv2_b, act=1)                        # GELU(conv2), [B*Tp, d]
+        x = ops.gemm(col2, self.conv2_w, bias=self.conv2_b, act=1, static_w=_STATIC_W)                        # GELU(conv2), [B*Tp, d]
         ops.add_pos_(x.view(B, Tp, d), self.pos)
         M = B * Tp
         scale = dh ** -0.5                                                                 # (q dh^-.25)(k dh^-.25)
         for L in self.layers:
             h = ops.layernorm(x, L["ln1_w"], L["ln1_b"])
-            qkv = ops.gemm(h, L["wqkv"], bias=L["bqkv"])
+            qkv = ops.gemm(h, L["wqkv"], bias=L["bqkv"], static_w=_STATIC_W)
             q = qkv[:, :d].view(B, Tp, H, dh)
             k = qkv[:, d:2 * d].view(B, Tp, H, dh)
             v = qkv[:, 2 * d:].view(B, Tp, H, dh)
             a, _ = ops.attn_fwd(q, k, v, causal=False, scale=scale)                        # no mask on padded frames (ref Q9)
-            ops.gemm(a.view(M, d), L["wo"], bias=L["bo"], residual=x, out=x)
+            ops.gemm(a.view(M, d), L["wo"], bias=L["bo"], residual=x, out=x, static_w=_STATIC_W)
             h = ops.layernorm(x, L["ln2_w"], L["ln2_b"])
-            f = ops.gemm(h, L["w1"], bias=L["b1"], act=1)
-            ops.gemm(f, L["w2"], bias=L["b2"], residual=x, out=x)
+            f = ops.gemm(h, L["w1"], bias=L["b1"], act=1, static_w=_STATIC_W)
+            ops.gemm(f, L["w2"], bias=L["b2"], residual=x, out=x, static_w=_STATIC_W)
         return ops.layernorm(x, self.lnp_w, self.lnp_b).view(B, Tp, d)
 
 
@@ -345,6 +347,7 @@ class LlamaLoRAB200:
         self.cfg, self.lora, self.arena = cfg, lora, arena
         self.device = _require_cuda(device)
         self.train_base = bool(train_base)
+        self._static_w = _STATIC_W and not self.train_base          # the base weights are frozen (LoRA / projector-only training)
         if self.train_base and lora is not None:
             raise NotImplementedError("full fine-tune together with LoRA adapters is not implemented (the reference recipes use one or the other)")
         dev = self.device
@@ -612,8 +615,8 @@ class LlamaLoRAB200:
         swap = bias is None and _swap_ab(x.shape[0], w.shape[0])
         if info is None:
             if swap:
-                return ops.gemm(w, x, residual=residual, out=out, transpose_out=True), None
-            return ops.gemm(x, w, residual=residual, out=out, bias=bias), None
+                return ops.gemm(w, x, residual=residual, out=out, transpose_out=True, static_w=self._static_w), None
+            return ops.gemm(x, w, residual=residual, out=out, bias=bias, static_w=self._static_w), None
         p, seed = self.dropout_p if self.dropout_active else 0.0, 0
         x_lora = x
         if p > 0.0:
@@ -621,9 +624,9 @@ class LlamaLoRAB200:
             x_lora = ops.dropout(x, p, seed)                                             # lora_A(dropout(x)): LoRA branch only
         t = _gemm_few_tiles(x_lora, info["a_cat"][li])                                   # T = x A_cat^T  [M, rpad]
         if swap:                                                                         # y^T tiles = W x^T + (s B_cat) T^T: same fused tile, operands swapped
-            y = ops.gemm(w, x, a2=info["b_cat"][li], b2=t, residual=residual, out=out, transpose_out=True)
+            y = ops.gemm(w, x, a2=info["b_cat"][li], b2=t, residual=residual, out=out, transpose_out=True, static_w=self._static_w)
         else:
-            y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias)   # fused base + LoRA tile
+            y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias, static_w=self._static_w)   # fused base + LoRA tile
         return y, (x_lora, t, p, seed)
 
     def _lin_bwd(self, dy, wT, gname: str, li: int, saved):
@@ -631,15 +634,15 @@ class LlamaLoRAB200:
         info = self.groups.get(gname)
         swap = _swap_ab(dy.shape[0], wT.shape[0])
         if info is None:
-            return ops.gemm(wT, dy, transpose_out=True) if swap else ops.gemm(dy, wT)
+            return ops.gemm(wT, dy, transpose_out=True, static_w=self._static_w) if swap else ops.gemm(dy, wT, static_w=self._static_w)
         x_lora, t, p, seed = saved
         u = _gemm_few_tiles(dy, info["b_catT"][li])                                      # U = dY (s B)  [M, rpad]
         if p > 0.0:
             dx = ops.dropout_bwd_add(ops.gemm(dy, wT), ops.gemm(u, info["a_catT"][li]), p, seed)
         elif swap:
-            dx = ops.gemm(wT, dy, a2=info["a_catT"][li], b2=u, transpose_out=True)
+            dx = ops.gemm(wT, dy, a2=info["a_catT"][li], b2=u, transpose_out=True, static_w=self._static_w)
         else:
-            dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li])                           # fused: one accumulator tile
+            dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li], static_w=self._static_w)                           # fused: one accumulator tile
         r, s = self.lora.r, self.lora.scaling
         for m in info["targets"]:
             off, col = info["roff"][m], info["cols"][m]
@@ -678,7 +681,7 @@ class LlamaLoRAB200:
             xn2, rstd2 = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=save)
             if self.fuse_swiglu:
                 hmid = torch.empty((M, cfg.ffn), device=x.device, dtype=BF16)
-                gu, sv_gu = ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid), None        # gu (blocked-64) and silu(g) * u from one epilogue
+                gu, sv_gu = ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid, static_w=self._static_w), None        # gu (blocked-64) and silu(g) * u from one epilogue
             else:
                 gu, sv_gu = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
                 hmid = ops.swiglu_fwd(gu)
@@ -720,7 +723,7 @@ class LlamaLoRAB200:
             xn2, _ = ops.rmsnorm_fwd(x2, Lw["ln2"], cfg.eps, need_rstd=False)
             if self.fuse_swiglu:
                 hmid = torch.empty((n, cfg.ffn), device=x.device, dtype=BF16)
-                ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid)
+                ops.gemm(xn2, Lw["wgu"], act=3, aux=hmid, static_w=self._static_w)
             else:
                 gu, _ = self._lin_fwd(xn2, Lw["wgu"], "gu", li)
                 hmid = ops.swiglu_fwd(gu)
@@ -749,7 +752,7 @@ class LlamaLoRAB200:
             pn = f"model.layers.{li}."
             # ---- MLP block: x3 = x2 + down(silu(g) * u)
             if self.fuse_swiglu_bwd and "down" not in self.groups:
-                dgu = ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"])                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
+                dgu = ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"], static_w=self._static_w)                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
             else:
                 dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
                 if tb:

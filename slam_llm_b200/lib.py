@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("workspace", _vp), ("workspace_bytes", _i64),
         ("tail_split", _i32), ("transpose_out", _i32),
         ("aux", _vp), ("ld_aux", _i64),
+        ("static_operands", _i32), ("reserved0", _i32),
     ]
 
 
@@ -126,8 +127,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.slam_abi_version() != 5:
-        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 5")
+    if lib.slam_abi_version() != 6:
+        raise RuntimeError(f"libslam_b200 ABI version {lib.slam_abi_version()} != 6")
     _lib = lib
     return lib
 

@@ -72,17 +72,19 @@ def _gemm_workspace(device: torch.device) -> torch.Tensor:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
          b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          act: int = 0, alpha: float = 1.0, out_f32: bool = False, block_n: int = 0, split_k: int = 1, tail_split: int = 0,
-         aux: Optional[torch.Tensor] = None, transpose_out: bool = False) -> torch.Tensor:
+         aux: Optional[torch.Tensor] = None, transpose_out: bool = False, static_w: bool = False) -> torch.Tensor:
     """out[M,N] = act(alpha*(a @ b.T + a2 @ b2.T) + bias) + residual ; a [M,K], b [N,K] bf16.
     tail_split: 0 = automatic, -1 = off, n > 1 = at most n k-slices per tail tile.
     act 3 / 4 = fused SwiGLU forward / backward on the blocked-64 gate/up layout (see slam_gemm_args.aux): act 3 returns gu and
-    writes h = silu(g) * u to aux [M, N/2]; act 4 reads gu from aux [M, 2N] and returns d(gu) [M, 2N] (the product dh is not stored)."""
+    writes h = silu(g) * u to aux [M, N/2]; act 4 reads gu from aux [M, 2N] and returns d(gu) [M, 2N] (the product dh is not stored).
+    static_w: the weight operand (`b`; `a` with transpose_out) is frozen - never written by a kernel that may still be in flight
+    (slam_gemm_args.static_operands): its first tiles are then requested under the tail of the preceding kernel."""
     _req(a, BF16, "gemm.a"); _req(b, BF16, "gemm.b")
     M, K1 = a.shape
     N = b.shape[0]
     assert b.shape[1] == K1, (a.shape, b.shape)
     if transpose_out:
-        return _gemm_swapped(a, b, out, a2, b2, residual, block_n)
+        return _gemm_swapped(a, b, out, a2, b2, residual, block_n, static_w)
     if split_k > 1:
         assert out_f32 and bias is None and residual is None and act == 0, "split_k needs a plain f32 output"
         if out is None:
@@ -127,6 +129,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
         g.aux, g.ld_aux = None, 0
     g.block_n = block_n
     g.transpose_out = 0
+    g.static_operands = 2 if static_w else 0
     g.split_k = split_k
     if tail_split == 0:
         tail_split = _TAIL_SPLIT_DEFAULT
@@ -147,7 +150,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     return out
 
 
-def _gemm_swapped(w, x, out, w2, x2, residual, block_n):
+def _gemm_swapped(w, x, out, w2, x2, residual, block_n, static_w=False):
     """transpose_out (swap-AB): returns y[Mx, Nw] = x @ w.T (+ x2 @ w2.T) (+ residual[Mx, Nw]) computed as tiles of (w @ x.T): the weight `w` [Nw, K]
     is the M operand (its rows fill 256-row CTA-pair tiles exactly), the activations `x` [Mx, K] the N operand."""
     Nw, K1 = w.shape
@@ -179,6 +182,7 @@ def _gemm_swapped(w, x, out, w2, x2, residual, block_n):
     g.m, g.n = Nw, Mx
     g.aux, g.ld_aux = None, 0
     g.block_n, g.split_k, g.tail_split, g.transpose_out = block_n, 1, -1, 1
+    g.static_operands = 1 if static_w else 0
     g.workspace, g.workspace_bytes = None, 0
     if _GEMM_LOG is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

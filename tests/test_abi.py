@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol(lib):
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/slam_b200.h but not exported"
     assert set(syms) == set(lib._SIGS), (set(syms) ^ set(lib._SIGS))
-    assert handle.slam_abi_version() == 5
+    assert handle.slam_abi_version() == 6
     assert handle.slam_launch_count() == 0          # nothing launched: no compute without a GPU
 
 

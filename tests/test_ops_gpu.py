@@ -437,6 +437,32 @@ def test_gemm_transpose_out_swap_ab(ops, tile):
     assert torch.equal(wide[:, 32: 32 + Nw].float(), want.to(BF16).float()) and float(wide[:, :32].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(1604, 64, 4096), (1604, 64, 6144), (300, 16, 1032), (128, 64, 14336), (4, 64, 4096), (1604, 40, 1024)])
+def test_gemm_thin_cluster(ops, shape):
+    """Thin products (N <= 64): a cluster of 8 CTAs per 128-row tile splits K and reduces the partial tiles through distributed shared memory
+    in rank order (csrc/gemm_thin.cuh).  Integer-valued inputs: exact in fp32 -> bit-exact after the bf16 rounding; `auto` must pick the
+    cluster kernel for these shapes and agree with the explicit choice and with the one-CTA-per-tile kernel."""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(17 + M + K)
+    a = torch.randint(-3, 4, (M, K), generator=g, device="cuda").to(BF16)
+    b = torch.randint(-3, 4, (N, K), generator=g, device="cuda").to(BF16)
+    want = (a.float() @ b.float().t() * 0.5).to(BF16)
+    y = ops.gemm(a, b, alpha=0.5, block_n=3000064)
+    assert y.shape == (M, N) and torch.equal(y, want)
+    assert torch.equal(ops.gemm(a, b, alpha=0.5), want)                      # auto
+    assert torch.equal(ops.gemm(a, b, alpha=0.5, block_n=64), want)          # the 128 x 64 one-CTA kernel
+    # real-valued inputs: deterministic (fixed reduction order) and within bf16 rounding of the fp32 product
+    a, b = rnd(M, K, seed=5), rnd(N, K, seed=6)
+    y1, y2 = ops.gemm(a, b, block_n=3000064), ops.gemm(a, b, block_n=3000064)
+    assert torch.equal(y1, y2)
+    ref = a.float() @ b.float().t()
+    assert float((y1.float() - ref).abs().max()) <= 0.01 * float(ref.abs().max()) + 1e-3
+    # a row-strided output (the LoRA products are written into slices of wider buffers)
+    wide = torch.zeros(M, N + 16, device="cuda", dtype=BF16)
+    ops.gemm(a, b, out=wide[:, 8: 8 + N], block_n=3000064)
+    assert torch.equal(wide[:, 8: 8 + N], y1) and float(wide[:, :8].abs().max()) == 0.0 and float(wide[:, 8 + N:].abs().max()) == 0.0
+
+
 def _rope_tables(S, dh, theta):
     inv = 1.0 / (theta ** (torch.arange(0, dh, 2, dtype=F32, device=dev()) / dh))
     fr = torch.outer(torch.arange(S, dtype=F32, device=dev()), inv)
