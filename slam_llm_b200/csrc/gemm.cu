@@ -488,12 +488,12 @@ static int launch_gemm(const slam_gemm_args* g, cudaStream_t stream) {
 static int g_trace_host_launch = 0;
 #endif
 
-template <int BLOCK_N>
+template <int BLOCK_N, int HALVES = 1>
 static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
-  using Cfg = GemmPairCfg<BLOCK_N>;
+  using Cfg = GemmPairCfg<BLOCK_N, HALVES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BLOCK_N, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm(pair): cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -502,17 +502,17 @@ static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
   }
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
-  if ((rc = make_tmap(&tmA, g->a, g->m, g->k1, g->lda, 128)) != 0) return rc;
+  if ((rc = make_tmap(&tmA, g->a, g->m, g->k1, g->lda, 128 * HALVES)) != 0) return rc;
   if ((rc = make_tmap(&tmB, g->b, g->n, g->k1, g->ldb, BLOCK_N / 2)) != 0) return rc;
   if (g->k2 > 0) {
-    if ((rc = make_tmap(&tmA2, g->a2, g->m, g->k2, g->lda2, 128)) != 0) return rc;
+    if ((rc = make_tmap(&tmA2, g->a2, g->m, g->k2, g->lda2, 128 * HALVES)) != 0) return rc;
     if ((rc = make_tmap(&tmB2, g->b2, g->n, g->k2, g->ldb2, BLOCK_N / 2)) != 0) return rc;
   } else {
     tmA2 = tmA;
     tmB2 = tmB;
   }
   GemmKParams p;
-  fill_kparams(g, 256, BLOCK_N, p);
+  fill_kparams(g, 256 * HALVES, BLOCK_N, p);
 #ifdef SLAM_GEMM_TRACE
   p.trace_id = g_trace_host_launch++;
 #endif
@@ -529,7 +529,7 @@ static int launch_gemm_pair(const slam_gemm_args* g, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_pair_kernel<BLOCK_N>, tmA, tmB, tmA2, tmB2, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_pair_kernel<BLOCK_N, HALVES>, tmA, tmB, tmA2, tmB2, p);
   if (le != cudaSuccess) {
     set_error("slam_gemm_bf16(pair): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
     return static_cast<int>(le);
@@ -696,6 +696,9 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
     case 2000192: return launch_gemm_pair<192>(g, st);
     case 2000160: return launch_gemm_pair<160>(g, st);
     case 2000128: return launch_gemm_pair<128>(g, st);
+    case 4000192:            // "pair512": 512 x 192 per SM pair, one accumulator set (plain / residual epilogue only)
+      SLAM_CHECK_ARG(g->act == 0 && g->split_k <= 1, "gemm: tile 4000192 supports act 0 without split_k only");
+      return launch_gemm_pair<192, 2>(g, st);
     default: set_error("gemm: unsupported tile %d", tile); return -1;
   }
 }

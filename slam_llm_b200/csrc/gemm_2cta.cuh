@@ -5,6 +5,12 @@
 // 2/3 of the bytes of the 128 x 256 single-CTA tile (16 KB A + 16 KB B-half instead of 16 KB + 32 KB per k-block), which is
 // what bounds the single-CTA mainloop (shared-memory fill + operand read bandwidth, and bytes in flight per SM).
 //
+// HALVES = 2 ("pair512"): each CTA owns 256 rows of A (two M = 256 instructions per k-step, same B tile), the pair a 512 x BLOCK_N tile with ONE
+// accumulator set (2 x BLOCK_N <= 512 TMEM columns, so no epilogue overlap).  Per MMA cycle an SM stages (256 + BLOCK_N / 2) rows instead of
+// 2 x (128 + BLOCK_N / 2): 21 % fewer operand bytes from L2 at BLOCK_N = 192 (cuBLAS runs 256 x 208 per CTA on these shapes:
+// profiles/r02_cublas_peek.txt).  Used when the whole GEMM is ONE round of such tiles (weights of 4096 rows x 1604 tokens = 72 tiles on 74 pairs),
+// where the second accumulator set of the 256-row schedule hid nothing but the first of two epilogues.
+//
 // Synchronisation (offsets are identical in both CTAs):
 //   full[s]    leader only; 1 arrival (leader producer, expect_tx = both CTAs' stage bytes); both producers' TMA loads
 //              complete_tx on it (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address);
@@ -16,15 +22,15 @@
 
 namespace slam {
 
-template <int BLOCK_N>
+template <int BLOCK_N, int HALVES = 1>
 struct GemmPairCfg {
-  static constexpr int ACC_STAGES = 2;
-  static constexpr int A_BYTES = 128 * GEMM_BK * 2;
+  static constexpr int ACC_STAGES = HALVES == 1 ? 2 : 1;
+  static constexpr int A_BYTES = HALVES * 128 * GEMM_BK * 2;
   static constexpr int B_BYTES = (BLOCK_N / 2) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
+  static constexpr int ACC_COLS = ACC_STAGES * HALVES * BLOCK_N;
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = GEMM_EPI_BYTES;
@@ -33,12 +39,13 @@ struct GemmPairCfg {
   static_assert((BLOCK_N / 2) % 8 == 0 && BLOCK_N % 16 == 0, "B half must be whole 8-row swizzle groups");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int HALVES = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
-  using Cfg = GemmPairCfg<BLOCK_N>;
+  using Cfg = GemmPairCfg<BLOCK_N, HALVES>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ROWS_CTA = 128 * HALVES;                    // rows of A (and of the output tile) per CTA
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -88,7 +95,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (threadIdx.x == 0) SLAM_TRACE(1);                      // prologue done (barriers, TMEM, cluster sync)
   pdl_trigger();
 
-  const int total_items = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // num_m_tiles counts 256-row pair tiles
+  const int total_items = p.num_m_tiles * p.num_n_tiles * p.ksplit;   // num_m_tiles counts pair tiles of 2 x ROWS_CTA rows
   const int nkb = p.kb1 + p.kb2;
 
   if (warp == 0) {
@@ -101,7 +108,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int tile = item / p.ksplit;
       const int m_tile = p.transpose_out ? tile / p.num_n_tiles : tile % p.num_m_tiles;
       const int n_tile = p.transpose_out ? tile % p.num_n_tiles : tile / p.num_m_tiles;
-      row_a = m_tile * 256 + static_cast<int>(rank) * 128;
+      row_a = m_tile * 2 * ROWS_CTA + static_cast<int>(rank) * ROWS_CTA;
       row_b = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
     };
     // Frozen operands (static_ops) do not depend on the preceding kernel: the first ring of their tiles is requested BEFORE
@@ -172,7 +179,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t aph = (it / ACC_STAGES) & 1u;
         mbar_wait_cluster(&tempty_bar[acc], aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * HALVES * BLOCK_N;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], ph);
           tc_fence_after();
@@ -181,6 +188,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, stage);
           const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, stage);
           umma_kblock_pair(d_tmem, a_lo, b_lo, idesc, kb > kb_begin ? 1u : 0u);
+          if constexpr (HALVES == 2) umma_kblock_pair(d_tmem + BLOCK_N, a_lo + 1024u, b_lo, idesc, kb > kb_begin ? 1u : 0u);   // rows 128..255 of each CTA: A tile + 16 KB
           umma_commit_pair_elect(empty_u + stage * 8);
           if (kb == kb_end - 1) umma_commit_pair_elect(tfull_u + acc * 8);
           if (lane == 0 && kb == kb_end - 1) SLAM_TRACE(it == 0 ? 5 : 6);  // last MMA of the first / of the latest tile issued
@@ -210,8 +218,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       if (e == 0 && lane == 0) SLAM_TRACE(it == 0 ? 7 : 9);             // accumulator of the first / latest tile complete
       const int n0 = n_tile * BLOCK_N;
-      const int row_base = m_tile * 256 + static_cast<int>(rank) * 128 + q * 32;
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const int row_base0 = m_tile * 2 * ROWS_CTA + static_cast<int>(rank) * ROWS_CTA + q * 32;
+      const uint32_t taddr0 = tmem_base + acc * HALVES * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      [[maybe_unused]] const int row_base = row_base0;
+      [[maybe_unused]] const uint32_t taddr = taddr0;
       auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
@@ -235,6 +245,29 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             gemm_epilogue_swiglu_fwd(p, ag, au, row_base, n0 + cg * 32, stg, lane);
           }
+        }
+        continue;
+      }
+      if constexpr (HALVES == 2) {
+        // 2 x NCH chunks per lane quarter (accumulator half u / NCH = rows +128), shared by the two warps of the quarter; act 0 only
+#pragma unroll 1
+        for (int u = h; u < 2 * NCH; u += 2) {
+          const int half = u / NCH, c = u % NCH;
+          const int rb = row_base0 + half * 128;
+          uint4 rsd[4];
+          gemm_residual_prefetch(p, rb, lane, n0 + c * 32, rsd);
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + half * BLOCK_N + c * 32, r);
+          tmem_ld_wait();
+          if (u + 2 >= 2 * NCH) release_tmem();
+          float accv[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
+          gemm_epilogue_chunk(p, accv, rsd, rb, n0 + c * 32, stg, lane);
+        }
+        if (e == 0 && lane == 0) {
+          SLAM_TRACE(it == 0 ? 8 : 10);
+          SLAM_TRACE_V(13, it + 1);
         }
         continue;
       }

@@ -16,6 +16,7 @@ data-parallel exchange is one NCCL all-reduce and the optimizer is one kernel.
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 from typing import Dict, List, Optional, Tuple
@@ -95,6 +96,19 @@ def _swap_ab(tokens: int, features: int) -> bool:
         return False
     pad = (-tokens) % 256
     return pad * 25 > tokens                      # more than 4 % of a pair grid would be padding rows
+
+
+_PAIR512 = os.environ.get("SLAM_PAIR512", "long")               # "0" never, "long" K >= 8192, "all" whenever the GEMM is one round of 512-row tiles
+
+
+@functools.lru_cache(maxsize=None)
+def _swap_tile(tokens: int, features: int, k: int) -> int:
+    """slam_gemm_args.block_n for a swap-AB GEMM: the 512 x 192 pair tile (one accumulator set, 21 % fewer operand bytes per MMA cycle) when the
+    whole product is ONE round of such tiles - e.g. 4096 weight rows x 1604 tokens = 8 x 9 = 72 tiles on 74 SM pairs - else 0 (automatic)."""
+    if _PAIR512 == "0" or features % 512 != 0 or (_PAIR512 != "all" and k < 8192):
+        return 0
+    pairs = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
+    return 4000192 if (features // 512) * ((tokens + 191) // 192) <= pairs else 0
 
 
 def _require_cuda(device) -> torch.device:
@@ -615,7 +629,8 @@ class LlamaLoRAB200:
         swap = bias is None and _swap_ab(x.shape[0], w.shape[0])
         if info is None:
             if swap:
-                return ops.gemm(w, x, residual=residual, out=out, transpose_out=True, static_w=self._static_w), None
+                return ops.gemm(w, x, residual=residual, out=out, transpose_out=True, static_w=self._static_w,
+                                block_n=_swap_tile(x.shape[0], w.shape[0], w.shape[1])), None
             return ops.gemm(x, w, residual=residual, out=out, bias=bias, static_w=self._static_w), None
         p, seed = self.dropout_p if self.dropout_active else 0.0, 0
         x_lora = x
@@ -624,7 +639,8 @@ class LlamaLoRAB200:
             x_lora = ops.dropout(x, p, seed)                                             # lora_A(dropout(x)): LoRA branch only
         t = _gemm_few_tiles(x_lora, info["a_cat"][li])                                   # T = x A_cat^T  [M, rpad]
         if swap:                                                                         # y^T tiles = W x^T + (s B_cat) T^T: same fused tile, operands swapped
-            y = ops.gemm(w, x, a2=info["b_cat"][li], b2=t, residual=residual, out=out, transpose_out=True, static_w=self._static_w)
+            y = ops.gemm(w, x, a2=info["b_cat"][li], b2=t, residual=residual, out=out, transpose_out=True, static_w=self._static_w,
+                         block_n=_swap_tile(x.shape[0], w.shape[0], w.shape[1]))
         else:
             y = ops.gemm(x, w, a2=t, b2=info["b_cat"][li], residual=residual, out=out, bias=bias, static_w=self._static_w)   # fused base + LoRA tile
         return y, (x_lora, t, p, seed)
@@ -634,13 +650,15 @@ class LlamaLoRAB200:
         info = self.groups.get(gname)
         swap = _swap_ab(dy.shape[0], wT.shape[0])
         if info is None:
-            return ops.gemm(wT, dy, transpose_out=True, static_w=self._static_w) if swap else ops.gemm(dy, wT, static_w=self._static_w)
+            return (ops.gemm(wT, dy, transpose_out=True, static_w=self._static_w, block_n=_swap_tile(dy.shape[0], wT.shape[0], wT.shape[1])) if swap
+                    else ops.gemm(dy, wT, static_w=self._static_w))
         x_lora, t, p, seed = saved
         u = _gemm_few_tiles(dy, info["b_catT"][li])                                      # U = dY (s B)  [M, rpad]
         if p > 0.0:
             dx = ops.dropout_bwd_add(ops.gemm(dy, wT), ops.gemm(u, info["a_catT"][li]), p, seed)
         elif swap:
-            dx = ops.gemm(wT, dy, a2=info["a_catT"][li], b2=u, transpose_out=True, static_w=self._static_w)
+            dx = ops.gemm(wT, dy, a2=info["a_catT"][li], b2=u, transpose_out=True, static_w=self._static_w,
+                          block_n=_swap_tile(dy.shape[0], wT.shape[0], wT.shape[1]))
         else:
             dx = ops.gemm(dy, wT, a2=u, b2=info["a_catT"][li], static_w=self._static_w)                           # fused: one accumulator tile
         r, s = self.lora.r, self.lora.scaling

@@ -410,11 +410,11 @@ def test_rmsnorm(ops, d):
     assert rel_err(dx, xr.grad + dres.float()) < 8e-3
 
 
-@pytest.mark.parametrize("tile", [0, 2000192, 2000224, 2000256, 128192, 128128])
+@pytest.mark.parametrize("tile", [0, 2000192, 2000224, 2000256, 128192, 128128, 4000192])
 def test_gemm_transpose_out_swap_ab(ops, tile):
     """transpose_out: the WEIGHT is the M operand (CTA-pair tiles without row padding), tokens are the N operand; the result still lands as
     y[tokens, features] = x W^T + x2 W2^T + residual.  Integer-valued inputs: exact in fp32 accumulation -> bit-exact after bf16 rounding."""
-    Mx, Nw, K, r = 1604, 768, 320, 64
+    Mx, Nw, K, r = 1604, 768, 320, 64                     # (768 weight rows: the 512-row tiles of 4000192 run half empty in their second row block)
     g = torch.Generator(device="cuda").manual_seed(91)
     x = torch.randint(-3, 4, (Mx, K), generator=g, device="cuda").to(BF16)
     w = torch.randint(-3, 4, (Nw, K), generator=g, device="cuda").to(BF16)
@@ -461,6 +461,29 @@ def test_gemm_thin_cluster(ops, shape):
     wide = torch.zeros(M, N + 16, device="cuda", dtype=BF16)
     ops.gemm(a, b, out=wide[:, 8: 8 + N], block_n=3000064)
     assert torch.equal(wide[:, 8: 8 + N], y1) and float(wide[:, :8].abs().max()) == 0.0 and float(wide[:, 8 + N:].abs().max()) == 0.0
+
+
+def test_gemm_pair512_single_round(ops):
+    """Tile 4000192 ("pair512": 512 x 192 per SM pair, one accumulator set) on the shape it is used for - 4096 weight rows x 1604 tokens = 72 tiles,
+    one round - with a long K, the LoRA segment and the residual; bit-exact on integer-valued inputs, equal to the 256-row schedule otherwise."""
+    Mx, Nw, K, r = 1604, 4096, 2048, 64
+    g = torch.Generator(device="cuda").manual_seed(123)
+    x = torch.randint(-2, 3, (Mx, K), generator=g, device="cuda").to(BF16)
+    w = torch.randint(-2, 3, (Nw, K), generator=g, device="cuda").to(BF16)
+    x2 = torch.randint(-2, 3, (Mx, r), generator=g, device="cuda").to(BF16)
+    w2 = torch.randint(-2, 3, (Nw, r), generator=g, device="cuda").to(BF16)
+    res = torch.randint(-8, 9, (Mx, Nw), generator=g, device="cuda").to(BF16)
+    want = (x.float() @ w.float().t() + x2.float() @ w2.float().t() + res.float()).to(BF16)
+    y = ops.gemm(w, x, a2=w2, b2=x2, residual=res, transpose_out=True, block_n=4000192, static_w=True)
+    assert torch.equal(y, want)
+    xr, wr = rnd(Mx, K, seed=31), rnd(Nw, K, scale=0.05, seed=32)
+    a = ops.gemm(wr, xr, residual=res, transpose_out=True, block_n=4000192)
+    b = ops.gemm(wr, xr, residual=res, transpose_out=True, block_n=2000192)
+    assert torch.equal(a, b)                                 # same k order per output element: identical fp32 accumulation
+    # several tiles per pair (no accumulator double buffering: the MMA waits for the epilogue): 8192 weight rows = 144 tiles on 74 pairs
+    w8 = torch.randint(-2, 3, (8192, 256), generator=g, device="cuda").to(BF16)
+    x8 = torch.randint(-2, 3, (Mx, 256), generator=g, device="cuda").to(BF16)
+    assert torch.equal(ops.gemm(w8, x8, transpose_out=True, block_n=4000192), (x8.float() @ w8.float().t()).to(BF16))
 
 
 def _rope_tables(S, dh, theta):
