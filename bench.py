@@ -717,7 +717,7 @@ def run_ours(args):
             "step_achieved_tflops": round(fl["total"] / (ms_per_step / 1e3) / 1e12, 1)}
     # DRAM bytes per GEMM launch: from the committed ncu pass over one eager step of this workload (tools/profile_round2.sh ->
     # tools/step_kernel_table.py); hardware counters cannot be read inside this process, so the number is per capture, not per run
-    for traffic_file, key in (("r02b_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")), ("r02_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")),
+    for traffic_file, key in (("r02c_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")), ("r02b_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")), ("r02_step_kernels.json", ("gemm_family", "dram_bytes_per_launch")),
                               ("r01_gemm_traffic.json", ("dram_bytes_per_launch",))):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))

@@ -44,7 +44,7 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["time_s"]):
     rows.append(dict(kernel=k, share=a["time_s"] / tot, launches=a["launches"], total_ms=a["time_s"] * 1e3, avg_us=a["time_s"] / a["launches"] * 1e6,
                      dram_mb_per_launch=a["dram_bytes"] / a["launches"] / 1e6, dram_gbs=gbs, hbm_frac=gbs / peak,
                      tensor_pipe_pct=a["tensor_w"] / a["time_s"] if a["time_s"] > 0 else 0.0))
-gemm = [r for r in rows if "gemm_tcgen05" in r["kernel"]]
+gemm = [r for r in rows if "gemm_tcgen05" in r["kernel"] or "gemm_thin_cluster" in r["kernel"]]
 gl = sum(r["launches"] for r in gemm) or 1
 gt = sum(r["total_ms"] for r in gemm) or 1.0
 summary = dict(source=path, hbm_peak_gbs=peak, launches=len(per), kernel_time_ms_under_ncu=tot * 1e3,
