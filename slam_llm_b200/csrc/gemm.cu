@@ -669,10 +669,11 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
     SLAM_CHECK_ARG(g->aux != nullptr && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0 && g->ld_aux % 8 == 0 && !g->out_f32 &&
                        g->bias == nullptr && g->residual == nullptr && g->split_k <= 1,
                    "gemm: fused SwiGLU needs a 16-byte aligned aux, a bf16 output and no bias/residual/split_k");
-    SLAM_CHECK_ARG(g->act == 3 ? g->n % 128 == 0 : g->n % 64 == 0, "gemm: fused SwiGLU needs whole blocked-64 groups (n=%d)", g->n);
+    const int feat = g->transpose_out != 0 ? g->m : g->n;          // the feature dimension of the product (swap-AB: the rows)
+    SLAM_CHECK_ARG(g->act == 3 ? feat % 128 == 0 : feat % 64 == 0, "gemm: fused SwiGLU needs whole blocked-64 groups (features=%d)", feat);
   }
-  SLAM_CHECK_ARG(g->transpose_out == 0 || (!g->out_f32 && g->act == 0 && g->bias == nullptr && g->split_k <= 1),
-                 "gemm: transpose_out needs a bf16 output and no bias / activation / split_k");
+  SLAM_CHECK_ARG(g->transpose_out == 0 || (!g->out_f32 && (g->act == 0 || g->act == 4) && g->bias == nullptr && g->split_k <= 1),
+                 "gemm: transpose_out needs a bf16 output, act 0 or 4 (SwiGLU backward) and no bias / split_k");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int tile = g->block_n;   // 0 = auto; BLOCK_N alone (64/128/192/256) = 128-row tile; BLOCK_M*1000+BLOCK_N = explicit
   if (tile == 3000064) {   // thin cluster kernel, explicitly
@@ -681,6 +682,10 @@ extern "C" int slam_gemm_bf16(const slam_gemm_args* g, void* stream) {
     return launch_gemm_thin(g, st);
   }
   if (tile == 0 && thin_cluster_applies(g)) return launch_gemm_thin(g, st);
+  if (g->transpose_out != 0 && g->act == 4) {     // swap-AB SwiGLU backward lives in the 256-row CTA-pair kernels only
+    if (tile == 0) tile = 2000192;
+    SLAM_CHECK_ARG(tile >= 2000000 && tile < 3000000, "gemm: transpose_out with act 4 needs a CTA-pair tile (2000000 + BLOCK_N), got %d", tile);
+  }
   if (tile == 0) tile = pick_tile(g->m, g->n, g->k1 + g->k2, g->workspace != nullptr && g->tail_split >= 0 && g->split_k <= 1 && g->act < 3, g->split_k <= 1, g->act == 3, g->act == 4);
   SLAM_CHECK_ARG(g->act != 3 || (tile % 1000) % 128 == 0, "gemm: SwiGLU forward needs a tile of 128 or 256 columns (tile %d)", tile);
   if (tile < 1000) tile += 128 * 1000;   // (2000000 + BLOCK_N = CTA-pair kernel)

@@ -274,8 +274,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll 1
       for (int c = h; c < NCH; c += 2) {
         uint4 rsd[4], rsd2[4];
-        if (p.act == 4) gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
-        else gemm_residual_prefetch(p, row_base, lane, n0 + c * 32, rsd);
+        if (p.act == 4) {
+          if (p.transpose_out) gemm_swiglu_bwd_prefetch_t(p, row_base, lane, n0 + c * 32, rsd, rsd2);
+          else gemm_swiglu_bwd_prefetch(p, row_base + lane, n0 + c * 32, rsd, rsd2);
+        } else {
+          gemm_residual_prefetch(p, row_base, lane, n0 + c * 32, rsd);
+        }
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -283,8 +287,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float accv[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t) accv[t] = __uint_as_float(r[t]);
-        if (p.act == 4) gemm_epilogue_swiglu_bwd(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
-        else gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
+        if (p.act == 4) {
+          if (p.transpose_out) gemm_epilogue_swiglu_bwd_t(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
+          else gemm_epilogue_swiglu_bwd(p, accv, rsd, rsd2, row_base, n0 + c * 32, stg, lane);
+        } else {
+          gemm_epilogue_chunk(p, accv, rsd, row_base, n0 + c * 32, stg, lane);
+        }
       }
       if (e == 0 && lane == 0) {
         SLAM_TRACE(it == 0 ? 8 : 10);                                     // epilogue of the first / latest tile done (warp 4's share)

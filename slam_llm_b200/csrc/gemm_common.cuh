@@ -325,4 +325,73 @@ __device__ __forceinline__ void gemm_epilogue_swiglu_bwd(const GemmKParams& p, c
   gemm_store_chunk_bf16(out, p.ldo, p.M, 2 * p.N, pdu, row_base, col_g + 64, stg, lane);
 }
 
+// act 4 with transpose_out (swap-AB d_down: the WEIGHT W_down^T [F, d] is the M operand): the accumulator chunk is dh for 32 FEATURES (rows
+// row_base ..., all inside one 64-feature block) x 32 tokens (columns col0 ...).  gu and d(gu) are [token][2F] (blocked-64) in memory, so - like the
+// transposed residual - the warp fetches gate / up in the memory layout (rg[i] / ru[i] = 8 consecutive features of token col0 + 8 i + lane / 4,
+// starting at feature row_base + 8 (lane % 4)) and transposes through its staging tile.
+__device__ __forceinline__ void gemm_swiglu_bwd_prefetch_t(const GemmKParams& p, int row_base, int lane, int col0, uint4 (&rg)[4], uint4 (&ru)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) rg[g] = ru[g] = make_uint4(0u, 0u, 0u, 0u);
+  const int f0 = row_base + 8 * (lane & 3);
+  if (f0 >= p.M) return;
+  const long long fcol = static_cast<long long>(f0 >> 6) * 128 + (f0 & 63);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = col0 + 8 * i + (lane >> 2);
+    if (c < p.N) {
+      const bf16* src = p.aux + static_cast<long long>(c) * p.ld_aux + fcol;
+      rg[i] = *reinterpret_cast<const uint4*>(src);
+      ru[i] = *reinterpret_cast<const uint4*>(src + 64);
+    }
+  }
+}
+__device__ __forceinline__ void gemm_epilogue_swiglu_bwd_t(const GemmKParams& p, const float (&acc)[32], const uint4 (&rg)[4], const uint4 (&ru)[4],
+                                                           int row_base, int col0, uint8_t* stg, int lane) {
+  const int piece = lane & 3, cl = lane >> 2;
+  float g[32], u[32];
+  // memory layout -> thread = feature: element e = token col0 + e
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece) = rg[i];
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < 32; ++e) g[e] = __bfloat162float(*reinterpret_cast<const bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece) = ru[i];
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < 32; ++e) u[e] = __bfloat162float(*reinterpret_cast<const bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane));
+  __syncwarp();
+  // d(gate) goes out first; d(up) overwrites u[] and follows
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const float d = __bfloat162float(__float2bfloat16_rn(acc[e] * p.alpha));     // dh rounded to bf16 like the stored tensor (slam_swiglu_bwd)
+    float dg, du;
+    swiglu_bwd_elem(g[e], u[e], d, dg, du);
+    *reinterpret_cast<bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane) = __float2bfloat16_rn(dg);
+    u[e] = du;
+  }
+  __syncwarp();
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  const int f0 = row_base + 8 * piece;
+  const long long fcol = static_cast<long long>(f0 >> 6) * 128 + (f0 & 63);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = col0 + 8 * i + cl;
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece);
+    if (c < p.N && f0 < p.M) *reinterpret_cast<uint4*>(out + static_cast<long long>(c) * p.ldo + fcol) = val;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < 32; ++e) *reinterpret_cast<bf16*>(stg + e * GEMM_EPI_PITCH + 2 * lane) = __float2bfloat16_rn(u[e]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = col0 + 8 * i + cl;
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + (8 * i + cl) * GEMM_EPI_PITCH + 16 * piece);
+    if (c < p.N && f0 < p.M) *reinterpret_cast<uint4*>(out + static_cast<long long>(c) * p.ldo + fcol + 64) = val;
+  }
+  __syncwarp();
+}
+
 }  // namespace slam

@@ -98,6 +98,8 @@ def _swap_ab(tokens: int, features: int) -> bool:
     return pad * 25 > tokens                      # more than 4 % of a pair grid would be padding rows
 
 
+_SWAP_DDOWN = os.environ.get("SLAM_SWAP_DDOWN", "0") != "0"      # swap-AB for the fused-SwiGLU-backward GEMM (d_down): measured +0.3 ... +0.6 ms per step
+                                                                  # (profiles/r02_ab_swap_ddown.log), so off; the kernel path stays (tested, ABI-documented)
 _PAIR512 = os.environ.get("SLAM_PAIR512", "long")               # "0" never, "long" K >= 8192, "all" whenever the GEMM is one round of 512-row tiles
 
 
@@ -770,7 +772,8 @@ class LlamaLoRAB200:
             pn = f"model.layers.{li}."
             # ---- MLP block: x3 = x2 + down(silu(g) * u)
             if self.fuse_swiglu_bwd and "down" not in self.groups:
-                dgu = ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"], static_w=self._static_w)                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
+                dgu = (ops.gemm(Lw["wdT"], dx, act=4, aux=kp["gu"], transpose_out=True, static_w=self._static_w) if _SWAP_DDOWN and _swap_ab(dx.shape[0], Lw["wdT"].shape[0])
+                       else ops.gemm(dx, Lw["wdT"], act=4, aux=kp["gu"], static_w=self._static_w))                  # dh = dY W_down stays in TMEM: the epilogue emits d(gu)
             else:
                 dhmid = self._lin_bwd(dx, Lw["wdT"], "down", li, kp["sv_d"])
                 if tb:

@@ -84,7 +84,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     N = b.shape[0]
     assert b.shape[1] == K1, (a.shape, b.shape)
     if transpose_out:
-        return _gemm_swapped(a, b, out, a2, b2, residual, block_n, static_w)
+        return _gemm_swapped(a, b, out, a2, b2, residual, block_n, static_w, act, aux)
     if split_k > 1:
         assert out_f32 and bias is None and residual is None and act == 0, "split_k needs a plain f32 output"
         if out is None:
@@ -150,15 +150,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None
     return out
 
 
-def _gemm_swapped(w, x, out, w2, x2, residual, block_n, static_w=False):
+def _gemm_swapped(w, x, out, w2, x2, residual, block_n, static_w=False, act=0, aux=None):
     """transpose_out (swap-AB): returns y[Mx, Nw] = x @ w.T (+ x2 @ w2.T) (+ residual[Mx, Nw]) computed as tiles of (w @ x.T): the weight `w` [Nw, K]
-    is the M operand (its rows fill 256-row CTA-pair tiles exactly), the activations `x` [Mx, K] the N operand."""
+    is the M operand (its rows fill 256-row CTA-pair tiles exactly), the activations `x` [Mx, K] the N operand.
+    act 4 (fused SwiGLU backward): the product is dh [Mx, Nw = F] (never stored), aux = gu [Mx, 2F], returns d(gu) [Mx, 2F]."""
     Nw, K1 = w.shape
     Mx = x.shape[0]
+    assert act in (0, 4), "transpose_out supports act 0 and 4"
+    out_cols = 2 * Nw if act == 4 else Nw
     if out is None:
-        out = torch.empty((Mx, Nw), device=w.device, dtype=BF16)
+        out = torch.empty((Mx, out_cols), device=w.device, dtype=BF16)
     _req(out, BF16, "gemm.out")
-    assert tuple(out.shape) == (Mx, Nw) and out.stride(1) == 1
+    assert tuple(out.shape) == (Mx, out_cols) and out.stride(1) == 1
     g = _l.GemmArgs()
     g.a, g.lda = w.data_ptr(), _row_major_2d(w, "gemm.a")
     g.b, g.ldb = x.data_ptr(), _row_major_2d(x, "gemm.b")
@@ -172,7 +175,7 @@ def _gemm_swapped(w, x, out, w2, x2, residual, block_n, static_w=False):
     else:
         g.k2 = 0
     g.out, g.ldo = out.data_ptr(), _row_major_2d(out, "gemm.out")
-    g.out_f32, g.act, g.bias, g.alpha = 0, 0, None, 1.0
+    g.out_f32, g.act, g.bias, g.alpha = 0, act, None, 1.0
     if residual is not None:
         _req(residual, BF16, "gemm.residual")
         assert tuple(residual.shape) == (Mx, Nw)
@@ -180,7 +183,12 @@ def _gemm_swapped(w, x, out, w2, x2, residual, block_n, static_w=False):
     else:
         g.residual, g.ldr = None, 0
     g.m, g.n = Nw, Mx
-    g.aux, g.ld_aux = None, 0
+    if act == 4:
+        _req(aux, BF16, "gemm.aux")
+        assert tuple(aux.shape) == (Mx, 2 * Nw) and residual is None and w2 is None
+        g.aux, g.ld_aux = aux.data_ptr(), _row_major_2d(aux, "gemm.aux")
+    else:
+        g.aux, g.ld_aux = None, 0
     g.block_n, g.split_k, g.tail_split, g.transpose_out = block_n, 1, -1, 1
     g.static_operands = 1 if static_w else 0
     g.workspace, g.workspace_bytes = None, 0

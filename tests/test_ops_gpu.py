@@ -463,6 +463,19 @@ def test_gemm_thin_cluster(ops, shape):
     assert torch.equal(wide[:, 8: 8 + N], y1) and float(wide[:, :8].abs().max()) == 0.0 and float(wide[:, 8 + N:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,F,K,tile", [(1604, 1792, 512, 0), (1604, 1792, 512, 2000256), (300, 512, 256, 2000192), (77, 128, 64, 2000160)])
+def test_gemm_fused_swiglu_bwd_swapped(ops, M, F, K, tile):
+    """act 4 with transpose_out (swap-AB d_down): W_down^T [F, K] is the M operand, dY [M, K] the N operand, gate / up and d(gu) are read / written
+    transposed through the epilogue's staging tile.  Same k order and the same per-element math as the non-swapped fused kernel: bit-identical."""
+    x, wg, wu = rnd(M, K, seed=194), rnd(F, K, scale=0.1, seed=195), rnd(F, K, scale=0.1, seed=196)
+    gu = ops.gemm(x, _block64(wg, wu), tail_split=-1)
+    dy, wd = rnd(M, K, seed=197), rnd(F, K, scale=0.1, seed=198)
+    want = ops.gemm(dy, wd, act=4, aux=gu, block_n=2000256)
+    got = ops.gemm(wd, dy, act=4, aux=gu, transpose_out=True, block_n=tile, static_w=True)
+    assert got.shape == (M, 2 * F) and torch.equal(got, want)
+    assert torch.equal(got, ops.swiglu_bwd(gu, ops.gemm(dy, wd, tail_split=-1), block=64))     # and to the unfused pair of kernels
+
+
 def test_gemm_pair512_single_round(ops):
     """Tile 4000192 ("pair512": 512 x 192 per SM pair, one accumulator set) on the shape it is used for - 4096 weight rows x 1604 tokens = 72 tiles,
     one round - with a long K, the LoRA segment and the residual; bit-exact on integer-valued inputs, equal to the 256-row schedule otherwise."""
