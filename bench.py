@@ -516,6 +516,44 @@ def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def measure_gemm_traffic(workload, budget_s=240.0):
+    """roofline.traffic measured in THIS run: one eager step of the same workload in a child process under `ncu`
+    (dram__bytes_read.sum + dram__bytes_write.sum of every GEMM launch, per launch).  Hardware counters cannot be read from inside the
+    timed process, so the child rebuilds the same step (same code, same shapes, same box); returns (bytes per launch | None, how)."""
+    import csv
+    import shutil
+    import subprocess
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with tempfile.TemporaryDirectory() as td:
+        log = os.path.join(td, "gemm_traffic.csv")
+        cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+               "--log-file", log, sys.executable, os.path.abspath(__file__), "--ncu-step", "--graph", "0", "--skip-cpu", "--skip-eager", "--skip-recipe",
+               "--skip-traffic", "--workload", workload]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=budget_s, env=env)
+        except subprocess.TimeoutExpired:
+            return None, f"ncu child exceeded {budget_s:.0f} s"
+        if not os.path.exists(log):
+            return None, f"ncu child wrote no log (rc={r.returncode})"
+        per = {}
+        for row in csv.DictReader(l for l in open(log) if not l.startswith("==")):
+            name = row.get("Kernel Name", "")
+            if "gemm_tcgen05" not in name and "gemm_thin_cluster" not in name:
+                continue
+            try:
+                per[row["ID"]] = per.get(row["ID"], 0.0) + float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1.0)
+            except (KeyError, ValueError):
+                continue
+    if not per:
+        return None, "no GEMM launches in the ncu log"
+    return round(sum(per.values()) / len(per)), f"measured in this run: ncu child process, one eager step of the same workload, {len(per)} GEMM launches"
+
+
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -734,6 +772,16 @@ def run_ours(args):
     if world == 1 and not args.skip_cpu:
         cb, _ = cpu_reference(wl, steps=2, warmup=0, budget_s=25.0)
         cb["value"] = round(cb["value"], 4)
+    if world == 1 and not args.skip_traffic:
+        torch.cuda.empty_cache()                                         # leave room for the child process's copy of the model
+        try:
+            traffic, how = measure_gemm_traffic(args.workload)
+        except Exception as e:                                           # never let the diagnostic take the bench line down
+            traffic, how = None, f"{type(e).__name__}: {e}"[:160]
+        if traffic is not None:
+            roof["traffic"], roof["traffic_source"] = traffic, how
+        else:
+            roof["traffic_source"] = f"{roof.get('traffic_source')} (in-run measurement unavailable: {how})"
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -759,6 +807,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-traffic", action="store_true", help="skip the in-run ncu child process that measures roofline.traffic (falls back to the committed ncu pass)")
     ap.add_argument("--ncu-step", action="store_true", help="run 3 warm-up steps, then ONE eager step between cudaProfilerStart/Stop, and exit")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the step from CUDA graphs (default), 0 = eager ctypes launches")
     ap.add_argument("--overlap", type=int, default=1, help="N>1: 1 = async all-reduce + deferred AdamW (default), 0 = blocking all-reduce")

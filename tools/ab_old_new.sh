@@ -3,7 +3,7 @@
 # alternating; then the in-kernel GEMM trace of the working tree's debug build (if present).
 cd "$(dirname "$0")/.."
 ROUNDS=${1:-2}
-B="--steps 20 --warmup 5 --skip-cpu --skip-eager --skip-recipe"
+B="--steps 20 --warmup 5 --skip-cpu --skip-eager --skip-recipe --skip-traffic"
 timeout 900 python -m pytest tests/test_ops_gpu.py -q -x -k "gemm" 2>&1 | tail -4 | cut -c1-300
 timeout 900 python -m pytest tests/test_step_parity_gpu.py tests/test_ref_parity_gpu.py -q -x 2>&1 | tail -3 | cut -c1-300
 for r in $(seq $ROUNDS); do

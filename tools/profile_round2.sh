@@ -6,7 +6,7 @@ set -u
 TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-B="python bench.py --ncu-step --graph 0 --skip-cpu --skip-eager --skip-recipe"
+B="python bench.py --ncu-step --graph 0 --skip-cpu --skip-eager --skip-recipe --skip-traffic"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
 timeout 900 ncu --profile-from-start off --metrics $M --clock-control none --csv --log-file $OUT/${TAG}_step_metrics.csv $B > $OUT/${TAG}_ncu_step.log 2>&1
 python tools/step_kernel_table.py $OUT/${TAG}_step_metrics.csv $OUT/${TAG}_step_kernels > /dev/null 2>&1
