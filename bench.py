@@ -516,18 +516,32 @@ def scale_breakdown(args, eng, dev_batch, lr, rank, world, dev, steps=20):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def parse_gemm_traffic(log):
+    """ncu `--csv --log-file` output -> {launch id: DRAM bytes read + written} for the GEMM kernels of this library."""
+    import csv
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for row in csv.DictReader(l for l in open(log) if not l.startswith("==")):
+        name = row.get("Kernel Name", "")
+        if "gemm_tcgen05" not in name and "gemm_thin_cluster" not in name:
+            continue
+        try:
+            per[row["ID"]] = per.get(row["ID"], 0.0) + float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1.0)
+        except (KeyError, ValueError):
+            continue
+    return per
+
+
 def measure_gemm_traffic(workload, budget_s=240.0):
     """roofline.traffic measured in THIS run: one eager step of the same workload in a child process under `ncu`
     (dram__bytes_read.sum + dram__bytes_write.sum of every GEMM launch, per launch).  Hardware counters cannot be read from inside the
     timed process, so the child rebuilds the same step (same code, same shapes, same box); returns (bytes per launch | None, how)."""
-    import csv
     import shutil
     import subprocess
     import tempfile
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return None, "ncu not found"
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     with tempfile.TemporaryDirectory() as td:
         log = os.path.join(td, "gemm_traffic.csv")
         cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
@@ -540,15 +554,7 @@ def measure_gemm_traffic(workload, budget_s=240.0):
             return None, f"ncu child exceeded {budget_s:.0f} s"
         if not os.path.exists(log):
             return None, f"ncu child wrote no log (rc={r.returncode})"
-        per = {}
-        for row in csv.DictReader(l for l in open(log) if not l.startswith("==")):
-            name = row.get("Kernel Name", "")
-            if "gemm_tcgen05" not in name and "gemm_thin_cluster" not in name:
-                continue
-            try:
-                per[row["ID"]] = per.get(row["ID"], 0.0) + float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1.0)
-            except (KeyError, ValueError):
-                continue
+        per = parse_gemm_traffic(log)
     if not per:
         return None, "no GEMM launches in the ncu log"
     return round(sum(per.values()) / len(per)), f"measured in this run: ncu child process, one eager step of the same workload, {len(per)} GEMM launches"

@@ -359,6 +359,27 @@ def test_reference_arm_only_rank0_works(monkeypatch, capsys):
     assert capsys.readouterr().out == ""                            # non-zero ranks exit without work or output
 
 
+def test_bench_gemm_traffic_parser_and_fallback(tmp_path, monkeypatch):
+    """roofline.traffic comes from an ncu child process of bench.py: the CSV parser keeps this library's GEMM launches only and sums read +
+    write bytes per launch id; without ncu (or when the child fails) the measurement reports why instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+    log = tmp_path / "m.csv"
+    log.write_text(
+        '==PROF== Connected to process 1\n'
+        '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"\n'
+        '"0","1","python","h","slam::logmel_kernel(float *)","1","7","(128, 1, 1)","(1, 1, 1)","0","10.0","s","dram__bytes_read.sum","Mbyte","5.0"\n'
+        '"1","1","python","h","void slam::gemm_tcgen05_pair_kernel<(int)192, (int)2>(CUtensorMap_st)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","s","dram__bytes_read.sum","Mbyte","100.5"\n'
+        '"1","1","python","h","void slam::gemm_tcgen05_pair_kernel<(int)192, (int)2>(CUtensorMap_st)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","s","dram__bytes_write.sum","Kbyte","500"\n'
+        '"2","1","python","h","slam::gemm_thin_cluster_kernel(CUtensorMap_st)","1","7","(192, 1, 1)","(104, 1, 1)","0","10.0","s","dram__bytes_read.sum","byte","1,000"\n'
+        '"2","1","python","h","slam::gemm_thin_cluster_kernel(CUtensorMap_st)","1","7","(192, 1, 1)","(104, 1, 1)","0","10.0","s","dram__bytes_write.sum","byte","24"\n')
+    per = bench.parse_gemm_traffic(str(log))
+    assert per == {"1": 100.5e6 + 500e3, "2": 1024.0}
+    monkeypatch.setattr("shutil.which", lambda name: None)
+    monkeypatch.setattr(os.path, "exists", lambda p, _orig=os.path.exists: False if str(p).endswith("/ncu") else _orig(p))
+    assert bench.measure_gemm_traffic("c3") == (None, "ncu not found")
+
+
 # ------------------------------------------------------------------------------------------------- reference recipe files, unchanged
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples/asr_librispeech"), reason="reference tree not present (GPU box)")
 def test_reference_recipe_files_import_unchanged_against_the_mirror(monkeypatch):
